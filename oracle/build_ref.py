@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Build the UNMODIFIED pyDVS Cython modules into ``oracle/_ref/`` (test infrastructure only).
+
+This is oracle tooling, not product code: only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import what it produces.
+
+Recipe (our own; the reference's ``setup.py`` is not run): for each of the three ``.pyx`` files the
+reference's ``setup.py:13-29`` lists, run the ``cython`` compiler on the source *where it lies* under
+``/root/reference/pydvs`` with the generated C going to ``oracle/_ref/pydvs/``, then ``gcc -shared`` it
+into a CPython extension next to it.  Nothing is copied from the reference; ``oracle/_ref/`` is
+git-ignored (build output) but travels to the GPU box with the snapshot.
+
+Importing the result (see ``oracle/ref_loader.py``) needs ``numpy.float = float`` set first for the
+uncoded/decode modules (``generate_spikes_uncoded.pyx:32``, ``decode_spikes.pyx:34``).
+"""
+import os
+import subprocess
+import sys
+import sysconfig
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SRC = os.environ.get("PYDVS_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref", "pydvs")
+MODULES = ("generate_spikes", "generate_spikes_uncoded", "decode_spikes")
+
+
+def ext_suffix():
+    return sysconfig.get_config_var("EXT_SUFFIX") or ".so"
+
+
+def built_paths():
+    return [os.path.join(OUT, m + ext_suffix()) for m in MODULES]
+
+
+def is_built():
+    return all(os.path.exists(p) for p in built_paths())
+
+
+def build(force=False, verbose=True):
+    """Returns True if oracle/_ref is available after the call."""
+    if is_built() and not force:
+        return True
+    src_dir = os.path.join(REF_SRC, "pydvs")
+    if not os.path.isdir(src_dir):
+        if verbose:
+            print("[oracle/_ref] reference sources not present at %s; skipping" % src_dir)
+        return is_built()
+    import numpy
+
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "__init__.py"), "w") as f:
+        f.write("# build output of oracle/build_ref.py (compiled pyDVS reference modules)\n")
+    py_inc = sysconfig.get_paths()["include"]
+    np_inc = numpy.get_include()
+    for mod in MODULES:
+        pyx = os.path.join(src_dir, mod + ".pyx")
+        c_out = os.path.join(OUT, mod + ".c")
+        so_out = os.path.join(OUT, mod + ext_suffix())
+        # language_level 3str is Cython 3's default; stated explicitly so the recipe is reproducible.
+        cy = [sys.executable, "-m", "cython", "--3str", "--module-name", "pydvs." + mod,
+              "-o", c_out, pyx]
+        r = subprocess.run(cy, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("cython failed for %s:\n%s\n%s" % (mod, r.stdout, r.stderr))
+        cc = ["gcc", "-shared", "-fPIC", "-O2", "-fwrapv", "-fno-strict-aliasing", "-w",
+              "-DNPY_NO_DEPRECATED_API=0", "-I", py_inc, "-I", np_inc, c_out, "-o", so_out]
+        r = subprocess.run(cc, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("gcc failed for %s:\n%s\n%s" % (mod, r.stdout, r.stderr))
+        os.remove(c_out)  # generated C is derived from reference text: never keep it around
+        if verbose:
+            print("[oracle/_ref] built", so_out)
+    return True
+
+
+if __name__ == "__main__":
+    ok = build(force="--force" in sys.argv)
+    sys.exit(0 if ok else 1)
