@@ -1,0 +1,783 @@
+// dvs_b200.cu -- sm_100a kernels + C-ABI of libpydvs_b200 (see include/pydvs_b200.h).
+//
+// Data path of one frame over S streams (DESIGN.md has the full account):
+//   K1 k_tile_pass   one CTA per tile (tile_rows full-width rows of one stream): 128-bit loads of
+//                    frame/reference(/threshold), threshold + sign split, k x k inhibition staged in
+//                    shared memory, reference (+ adaptive threshold) update written back in place,
+//                    ordered compaction of the spiking pixels into the tile's record list
+//                    (shuffle scans, 16-bit packed pos|neg counters) and the tile's per-slot event
+//                    counts (register histograms + redux.sync, or shared-memory atomics).
+//   K2 k_scan_*      exclusive scans of the per-tile counters -> CSR row pointers.
+//   K3 k_expand      one warp per (tile, polarity): ballot/popc expansion of records into
+//                    (x, y, t, p) events at their final, reference-ordered positions.
+// Everything is HBM-bound integer work: no tensor cores, no TMEM.
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "dvs_device.cuh"
+#include "dvs_tile_pass.cuh"
+#include "pydvs_b200.h"
+
+namespace dvs {
+
+// ================================================================================================
+// K1': (rows; cols; vals) lists -> tiles of one stream (make_spike_lists_* signatures)
+// ================================================================================================
+struct ListArgs {
+  const int16_t *pos, *neg;
+  long long n_pos, n_neg, pos_stride, neg_stride;
+  int chunk, n_pos_tiles, tiles, C;
+  EncArgs enc;
+  dvs_record *records;
+  uint32_t *tile_counts;
+  int32_t *status;
+};
+
+__global__ void __launch_bounds__(256) k_lists_to_tiles(const __grid_constant__ ListArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);  // n_slots + 1
+  const int nh = A.enc.n_slots + 1;
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  const bool is_pos = tile < A.n_pos_tiles;
+  const long long first = (long long)(is_pos ? tile : tile - A.n_pos_tiles) * A.chunk;
+  const long long total = is_pos ? A.n_pos : A.n_neg;
+  const int n = (int)max(0ll, min((long long)A.chunk, total - first));
+  const int16_t *src = is_pos ? A.pos : A.neg;
+  const long long stride = is_pos ? A.pos_stride : A.neg_stride;
+  for (int i = tid; i < nh; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  unsigned status = 0;
+  dvs_record *dst = A.records + (size_t)tile * A.chunk + (is_pos ? 0 : A.chunk - n);
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int row = (uint16_t)src[first + i], col = (uint16_t)src[stride + first + i];
+    const int val = src[2 * stride + first + i];
+    *reinterpret_cast<uint2 *>(dst + i) =
+        make_uint2((uint32_t)row | ((uint32_t)col << 16), (uint32_t)(val & 0xffff));
+    const int desc = enc_desc(A.enc, val, is_pos, status);
+    if (A.enc.mode == DVS_ENC_RATE || A.enc.mode == DVS_ENC_TIME) {
+      if (desc >= 0) atomicAdd(&hist[desc], 1u);
+    } else if (A.enc.mode != DVS_ENC_NONE) {
+      for (int jj = 0; jj < A.enc.n_slots; ++jj) {
+        unsigned inv;
+        const unsigned sm = bin_slotmask(A.enc, jj, inv);
+        if (desc & inv) status |= DVS_STATUS_SLOT_RANGE;
+        const int m = __popc((unsigned)desc & sm);
+        if (m) atomicAdd(&hist[jj], (unsigned)m);
+      }
+    }
+  }
+  if (status && A.status) atomicOr(A.status, (int)status);
+  __syncthreads();
+  for (int c = tid; c < A.C; c += blockDim.x) {
+    uint32_t v = 0;
+    if (c < 2) v = (c == (is_pos ? 0 : 1)) ? n : 0;
+    else {
+      const int slot = (c - 2) >> 1, pol = (c - 2) & 1;
+      if (pol == (is_pos ? 0 : 1)) {
+        if (A.enc.mode == DVS_ENC_RATE) {
+          for (int kk = slot + 1; kk <= A.enc.n_slots; ++kk) v += hist[kk];
+        } else v = hist[slot];
+      }
+    }
+    A.tile_counts[(size_t)c * A.tiles + tile] = v;
+  }
+}
+
+// ================================================================================================
+// K2: scans
+// ================================================================================================
+// one warp per (stream, component): exclusive scan over the stream's tiles (contiguous memory)
+__global__ void __launch_bounds__(256) k_scan_tiles(int n_rows, int tps, const uint32_t *__restrict__ counts,
+                                                    uint32_t *__restrict__ excl,
+                                                    uint32_t *__restrict__ totals) {
+  const int gw = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (gw >= n_rows) return;
+  const size_t base = (size_t)gw * tps;
+  uint32_t carry = 0;
+  for (int t0 = 0; t0 < tps; t0 += 32) {
+    const int t = t0 + lane;
+    const uint32_t v = t < tps ? counts[base + t] : 0;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(kFull, x, o);
+      if (lane >= o) x += y;
+    }
+    if (t < tps) excl[base + t] = carry + x - v;
+    carry += __shfl_sync(kFull, x, 31);
+  }
+  if (lane == 0) totals[gw] = carry;
+}
+
+// single CTA: CSR row pointers over (stream, slot, polarity) from the stream totals
+__global__ void __launch_bounds__(1024) k_scan_segments(int S, int n_slots, const uint32_t *__restrict__ totals,
+                                                        long long *__restrict__ seg_offsets) {
+  __shared__ long long wsum[32];
+  __shared__ long long carry_sm;
+  const int C = 2 + 2 * n_slots, per = 2 * n_slots;
+  const long long n = (long long)S * per;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long chunk = (n + blockDim.x - 1) / blockDim.x;
+  const long long lo = min(n, (long long)tid * chunk), hi = min(n, lo + chunk);
+  long long sum = 0;
+  for (long long i = lo; i < hi; ++i) sum += totals[(i / per) * C + 2 + (i % per)];
+  long long x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long y = __shfl_up_sync(kFull, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    long long w = wsum[lane], wx = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long y = __shfl_up_sync(kFull, wx, o);
+      if (lane >= o) wx += y;
+    }
+    wsum[lane] = wx - w;
+    if (lane == 31) carry_sm = wx;
+  }
+  __syncthreads();
+  long long run = wsum[warp] + x - sum;
+  for (long long i = lo; i < hi; ++i) {
+    seg_offsets[i] = run;
+    run += totals[(i / per) * C + 2 + (i % per)];
+  }
+  if (tid == 0) seg_offsets[n] = carry_sm;
+}
+
+// ================================================================================================
+// K3: expand records into events, one warp per (tile, polarity)
+// ================================================================================================
+struct ExpandArgs {
+  int S, tps, tile_px, C;
+  EncArgs enc;
+  const dvs_record *records;
+  const uint32_t *tile_counts, *tile_excl;
+  const long long *seg_offsets;
+  dvs_event *events;
+  long long event_cap;
+  int32_t *status;
+};
+
+__global__ void __launch_bounds__(256) k_expand(const __grid_constant__ ExpandArgs A) {
+  const int lane = threadIdx.x & 31;
+  const long long n_seg = (long long)A.S * A.enc.n_slots * 2;
+  if (A.seg_offsets[n_seg] > A.event_cap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && A.status) atomicOr(A.status, (int)DVS_STATUS_EVENT_OVERFLOW);
+    return;
+  }
+  const long long n_tasks = 2ll * A.S * A.tps;
+  const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bool bin_mode = A.enc.mode == DVS_ENC_TIME_BIN || A.enc.mode == DVS_ENC_TIME_BIN_THR;
+  unsigned status = 0;
+  for (long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < n_tasks;
+       task += warps_total) {
+    const long long tile = task >> 1;
+    const int pol = (int)(task & 1);
+    const int s = (int)(tile / A.tps), t = (int)(tile - (long long)s * A.tps);
+    const int n = (int)A.tile_counts[((size_t)s * A.C + pol) * A.tps + t];
+    if (n == 0) continue;
+    const dvs_record *rec = A.records + (size_t)tile * A.tile_px + (pol ? A.tile_px - n : 0);
+    for (int sb = 0; sb < A.enc.n_slots; sb += 32) {
+      const int jmine = sb + lane;
+      long long base = 0;
+      unsigned slotmask = 0;
+      if (jmine < A.enc.n_slots) {
+        base = A.seg_offsets[((long long)s * A.enc.n_slots + jmine) * 2 + pol] +
+               A.tile_excl[((size_t)s * A.C + 2 + 2 * jmine + pol) * A.tps + t];
+        if (bin_mode) { unsigned inv; slotmask = bin_slotmask(A.enc, jmine, inv); }
+      }
+      const int nj = min(32, A.enc.n_slots - sb);
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        uint2 r = make_uint2(0, 0);
+        int desc = (A.enc.mode == DVS_ENC_TIME) ? -1 : 0;
+        if (i < n) {
+          r = *reinterpret_cast<const uint2 *>(rec + i);
+          desc = enc_desc(A.enc, (int)(short)(r.y & 0xffff), pol == 0, status);
+        }
+        int jend = nj;
+        if (A.enc.mode == DVS_ENC_RATE) jend = min(nj, max(0, __reduce_max_sync(kFull, desc) - sb));
+        const uint32_t xy = (r.x >> 16) | (r.x << 16);  // record is (row, col); event is (x=col, y=row)
+        for (int jj = 0; jj < jend; ++jj) {
+          const unsigned sm = __shfl_sync(kFull, slotmask, jj);
+          const int m = enc_mult(A.enc, desc, sb + jj, sm);
+          const long long b = __shfl_sync(kFull, base, jj);
+          int tot, ex;
+          if (!bin_mode) {
+            const unsigned bal = __ballot_sync(kFull, m != 0);
+            tot = __popc(bal);
+            ex = __popc(bal & ((1u << lane) - 1u));
+          } else {
+            int x = m;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int y = __shfl_up_sync(kFull, x, o);
+              if (lane >= o) x += y;
+            }
+            tot = __shfl_sync(kFull, x, 31);
+            ex = x - m;
+          }
+          if (m) {
+            const uint2 ev = make_uint2(xy, (uint32_t)(sb + jj) | ((pol ? 0xffffu : 1u) << 16));
+            for (int q = 0; q < m; ++q) *reinterpret_cast<uint2 *>(A.events + b + ex + q) = ev;
+          }
+          if (lane == jj) base += tot;
+        }
+      }
+    }
+  }
+  status = __reduce_or_sync(kFull, status);
+  if (status && lane == 0 && A.status) atomicOr(A.status, (int)status);
+}
+
+// ================================================================================================
+// gather tile-local record lists of one stream into contiguous (rows; cols; vals) arrays
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_gather_split(int s, int tps, int tile_px, int C,
+                                                      const dvs_record *__restrict__ records,
+                                                      const uint32_t *__restrict__ counts,
+                                                      const uint32_t *__restrict__ excl,
+                                                      int16_t *pos_out, long long pos_stride,
+                                                      int16_t *neg_out, long long neg_stride) {
+  const int lane = threadIdx.x & 31;
+  const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < 2ll * tps;
+       task += warps_total) {
+    const int t = (int)(task >> 1), pol = (int)(task & 1);
+    const size_t ci = ((size_t)s * C + pol) * tps + t;
+    const int n = (int)counts[ci];
+    if (n == 0) continue;
+    const long long off = excl[ci];
+    const size_t tile = (size_t)s * tps + t;
+    const dvs_record *rec = records + tile * tile_px + (pol ? tile_px - n : 0);
+    int16_t *out = pol ? neg_out : pos_out;
+    const long long stride = pol ? neg_stride : pos_stride;
+    for (int i = lane; i < n; i += 32) {
+      const uint2 r = *reinterpret_cast<const uint2 *>(rec + i);
+      out[off + i] = (int16_t)(r.x & 0xffff);
+      out[stride + off + i] = (int16_t)(r.x >> 16);
+      out[2 * stride + off + i] = (int16_t)(r.y & 0xffff);
+    }
+  }
+}
+
+// ================================================================================================
+// unfused function-for-function kernels
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_thresholded_difference(const int16_t *__restrict__ curr,
+                                                                const int16_t *__restrict__ ref,
+                                                                const int16_t *__restrict__ thr_plane,
+                                                                int thr_scalar, int16_t *__restrict__ diff,
+                                                                int16_t *__restrict__ abs_diff,
+                                                                int16_t *__restrict__ spikes, long long n,
+                                                                int vec) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long q0 = g * 8;
+  if (q0 >= n) return;
+  const int nv = (int)min(8ll, n - q0);
+  uint32_t c[4], r[4], t[4] = {0, 0, 0, 0}, d_pk[4] = {0, 0, 0, 0}, a_pk[4] = {0, 0, 0, 0}, s_pk[4] = {0, 0, 0, 0};
+  load8_i16(curr, q0, nv, vec, c);
+  load8_i16(ref, q0, nv, vec, r);
+  if (thr_plane) load8_i16(thr_plane, q0, nv, vec, t);
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    if (p < nv) {
+      int T, negT;
+      if (thr_plane) { T = get16(t, p); negT = w16(-T); }
+      else { T = thr_scalar; negT = -T; }
+      int d, a, s;
+      threshold_px(get16(c, p), get16(r, p), T, negT, d, a, s);
+      set16(d_pk, p, d); set16(a_pk, p, a); set16(s_pk, p, s);
+    }
+  }
+  store8_i16(diff, q0, nv, vec, d_pk);
+  store8_i16(abs_diff, q0, nv, vec, a_pk);
+  store8_i16(spikes, q0, nv, vec, s_pk);
+}
+
+// one thread per k x k area; in place on spikes
+__global__ void __launch_bounds__(256) k_local_inhibition(int16_t *__restrict__ spikes,
+                                                          const int16_t *__restrict__ abs_diff, int S, int H,
+                                                          int W, int k) {
+  const int aw = W / k, ah = H / k;
+  const long long n_areas = (long long)S * aw * ah;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_areas) return;
+  const int ax = (int)(g % aw);
+  const long long rest = g / aw;
+  const int ay = (int)(rest % ah), s = (int)(rest / ah);
+  const size_t o = (size_t)s * H * W + (size_t)ay * k * W + (size_t)ax * k;
+  int best = abs_diff[o], br = 0, bc = 0;
+  for (int rr = 0; rr < k; ++rr)
+    for (int cc = 0; cc < k; ++cc) {
+      const int v = abs_diff[o + (size_t)rr * W + cc];
+      if (v > best) { best = v; br = rr; bc = cc; }
+    }
+  for (int rr = 0; rr < k; ++rr)
+    for (int cc = 0; cc < k; ++cc)
+      if (rr != br || cc != bc) spikes[o + (size_t)rr * W + cc] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_update_reference(const __grid_constant__ UpdateArgs U,
+                                                          const int16_t *__restrict__ abs_diff,
+                                                          const int16_t *__restrict__ spikes,
+                                                          const int16_t *__restrict__ ref_in,
+                                                          int16_t *__restrict__ ref_out, int16_t *thr,
+                                                          int16_t *thr_out, long long n, int vec,
+                                                          int32_t *status_out) {
+  const long long q0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (q0 >= n) return;
+  const int nv = (int)min(8ll, n - q0);
+  const bool adpt = U.mode == DVS_UPD_RATE_ADPT;
+  uint32_t a[4], s[4], r[4], t[4] = {0, 0, 0, 0}, rn[4] = {0, 0, 0, 0}, ts[4] = {0, 0, 0, 0}, tr[4] = {0, 0, 0, 0};
+  load8_i16(abs_diff, q0, nv, vec, a);
+  load8_i16(spikes, q0, nv, vec, s);
+  load8_i16(ref_in, q0, nv, vec, r);
+  if (adpt) load8_i16(thr, q0, nv, vec, t);
+  unsigned status = 0;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    if (p < nv) {
+      int th_state = get16(t, p), th_ret = th_state;
+      const int v = update_px(U, get16(a, p), get16(s, p), get16(r, p), th_state, th_ret, status);
+      set16(rn, p, v); set16(ts, p, th_state); set16(tr, p, th_ret);
+    }
+  }
+  store8_i16(ref_out, q0, nv, vec, rn);
+  if (adpt) {
+    store8_i16(thr, q0, nv, vec, ts);
+    if (thr_out != thr) store8_i16(thr_out, q0, nv, vec, tr);
+  }
+  if (status && status_out) atomicOr(status_out, (int)status);
+}
+
+// noise variants gs:428-473: mark sampled pixels, then one elementwise pass
+__global__ void __launch_bounds__(256) k_mark_samples(const int16_t *__restrict__ sample, long long n_sample,
+                                                      int W, int H, uint8_t *__restrict__ flags,
+                                                      int32_t *status_out) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_sample) return;
+  const int v = sample[g];
+  const int q = np_floordiv(v, W);
+  int r = w16(q), c = w16(v - q * W);  // sample // width, sample % width (int16 arrays)
+  if (r < 0) r += H;
+  if (c < 0) c += W;
+  if (r < 0 || r >= H || c < 0 || c >= W) { if (status_out) atomicOr(status_out, (int)DVS_STATUS_INDEX); return; }
+  flags[(size_t)r * W + c] = 1;
+}
+
+__global__ void __launch_bounds__(256) k_update_noise(int thresh_variant, const int16_t *__restrict__ abs_diff,
+                                                      const int16_t *__restrict__ spikes,
+                                                      const int16_t *__restrict__ ref_in,
+                                                      int16_t *__restrict__ ref_out, long long n, FastDiv dv,
+                                                      int max_time_ms, double hw, int hw_is_one,
+                                                      const uint8_t *__restrict__ lut, int lut_len,
+                                                      const uint8_t *__restrict__ flags, int32_t *status_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int a = abs_diff[i];
+  int mult;
+  if (thresh_variant) {
+    mult = w16(clip(w16(div_T(a, dv)), 0, max_time_ms));  // gs:463
+    if (flags[i]) mult = 0;                               // gs:469
+  } else {
+    int idx = a;
+    if (idx < 0) idx += lut_len;
+    if (idx < 0 || idx >= lut_len) { if (status_out) atomicOr(status_out, (int)DVS_STATUS_LUT_INDEX); mult = 0; }
+    else mult = lut[idx];                                 // gs:440
+    if (flags[i]) mult = w16(mult ^ 0xFF);                // gs:445
+  }
+  // gs:447 / gs:471: no clip; the thresh variant omits `* threshold`
+  ref_out[i] = (int16_t)w16(hist_weight(hw, hw_is_one != 0, ref_in[i]) + w16(spikes[i] * mult));
+}
+
+// DVSOperator::operator() cpp/dvs_op.cpp:12-31; explicit _rn intrinsics forbid FMA contraction
+__global__ void __launch_bounds__(256) k_step_f32(const float *__restrict__ src, float *__restrict__ diff,
+                                                  float *__restrict__ ref, float *__restrict__ thr, float relax,
+                                                  float up, float down, long long n, int vec) {
+  const long long q0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (q0 >= n) return;
+  float sv[4], rv[4], tv[4], dv[4];
+  const int nv = (int)min(4ll, n - q0);
+  if (vec && nv == 4) {
+    const float4 a = *reinterpret_cast<const float4 *>(src + q0), b = *reinterpret_cast<const float4 *>(ref + q0),
+                 c = *reinterpret_cast<const float4 *>(thr + q0);
+    sv[0] = a.x; sv[1] = a.y; sv[2] = a.z; sv[3] = a.w;
+    rv[0] = b.x; rv[1] = b.y; rv[2] = b.z; rv[3] = b.w;
+    tv[0] = c.x; tv[1] = c.y; tv[2] = c.z; tv[3] = c.w;
+  } else {
+    for (int p = 0; p < 4; ++p) {
+      sv[p] = p < nv ? src[q0 + p] : 0.f; rv[p] = p < nv ? ref[q0 + p] : 0.f; tv[p] = p < nv ? thr[q0 + p] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    float d = __fsub_rn(sv[p], rv[p]);
+    const bool test = (d < -tv[p]) || (d > tv[p]);
+    d = __fmul_rn(d, test ? 1.0f : 0.0f);
+    dv[p] = d;
+    rv[p] = __fadd_rn(__fmul_rn(relax, rv[p]), d);
+    tv[p] = test ? __fmul_rn(tv[p], up) : __fmul_rn(tv[p], down);
+  }
+  if (vec && nv == 4) {
+    if (diff) *reinterpret_cast<float4 *>(diff + q0) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    *reinterpret_cast<float4 *>(ref + q0) = make_float4(rv[0], rv[1], rv[2], rv[3]);
+    *reinterpret_cast<float4 *>(thr + q0) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+  } else {
+    for (int p = 0; p < nv; ++p) {
+      if (diff) diff[q0 + p] = dv[p];
+      ref[q0 + p] = rv[p]; thr[q0 + p] = tv[p];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_keys_from_events(const dvs_event *__restrict__ ev, long long n, int uncoded,
+                                                          int flag_shift, int data_shift, int data_mask,
+                                                          int16_t *__restrict__ keys) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint2 e = *reinterpret_cast<const uint2 *>(ev + i);
+  const int x = e.x & 0xffff, y = e.x >> 16, p = (short)(e.y >> 16);
+  keys[i] = (int16_t)spike_key(y, x, p > 0, uncoded, flag_shift, data_shift, data_mask);
+}
+
+}  // namespace dvs
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+using namespace dvs;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+namespace dvs {
+int set_error(int code, const char *msg) { return fail(code, msg); }
+}  // namespace dvs
+static int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return DVS_OK;
+}
+static FastDiv make_div(int T) {
+  FastDiv f;
+  f.T = T;
+  f.magic = (T >= 2) ? (unsigned)((0x100000000ull + (unsigned)T - 1) / (unsigned)T) : 0u;
+  return f;
+}
+static EncArgs make_enc(const dvs_enc_params *e) {
+  EncArgs E;
+  memset(&E, 0, sizeof(E));
+  if (!e) { E.mode = DVS_ENC_NONE; return E; }
+  E.mode = e->mode; E.uncoded = e->uncoded; E.threshold = e->threshold;
+  E.n_slots = e->mode == DVS_ENC_NONE ? 0 : e->n_slots;
+  E.u16_vals = e->u16_vals; E.lut_len = e->lut_len; E.lut = e->lut;
+  E.dv = make_div(e->threshold);
+  return E;
+}
+static int check_enc(const dvs_enc_params *e) {
+  if (!e || e->mode == DVS_ENC_NONE) return DVS_OK;
+  if (e->mode < 0 || e->mode > DVS_ENC_NONE) return fail(DVS_ERR_INVALID_ARGUMENT, "encoder mode");
+  if (e->n_slots < 0 || e->n_slots > kMaxSlots) return fail(DVS_ERR_UNSUPPORTED, "n_slots outside [0, 1024]");
+  if ((e->mode == DVS_ENC_TIME_BIN || e->mode == DVS_ENC_TIME_BIN_THR) && (!e->lut || e->lut_len <= 0))
+    return fail(DVS_ERR_INVALID_ARGUMENT, "time-binary encoders need a log2 table");
+  if (e->mode != DVS_ENC_TIME_BIN && e->threshold == 0)
+    return fail(DVS_ERR_INVALID_ARGUMENT, "encoder threshold is zero (reference: ZeroDivisionError)");
+  return DVS_OK;
+}
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int dvs_abi_version(void) { return DVS_ABI_VERSION; }
+const char *dvs_last_error_string(void) { return g_err; }
+
+int dvs_get_limits(dvs_limits *out) {
+  if (!out) return fail(DVS_ERR_INVALID_ARGUMENT, "null limits");
+  out->max_tile_px = kMaxTilePx; out->max_slots = kMaxSlots; out->max_width = 65535; out->sm_count = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int sm = 0;
+    if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) out->sm_count = sm;
+  }
+  cudaGetLastError();
+  return DVS_OK;
+}
+
+int dvs_choose_tile_rows(int32_t S, int32_t H, int32_t W, int32_t inh_k) {
+  const int k = inh_k > 1 ? inh_k : 1;
+  if (S <= 0 || H <= 0 || W <= 0 || (long long)W * k > kMaxTilePx) return -1;
+  const int target_px = 8192;
+  int rows = (target_px / W) / k * k;
+  if (rows < k) rows = k;
+  const int h_up = (H + k - 1) / k * k;
+  if (rows > h_up) rows = h_up;
+  // keep at least ~4 CTAs per SM in flight when the problem allows it
+  const long long want = 4ll * 148;
+  while (rows > k && (long long)S * ((H + rows - 1) / rows) < want) {
+    int nr = (rows / 2) / k * k;
+    if (nr < k) nr = k;
+    if (nr == rows) break;
+    rows = nr;
+  }
+  return rows;
+}
+
+static int fill_tiling(TileArgs &A, const dvs_tiling &t, int n_slots_or_none, int enc_mode) {
+  if (t.S <= 0 || t.H <= 0 || t.W <= 0 || t.tile_rows <= 0) return fail(DVS_ERR_INVALID_ARGUMENT, "tiling");
+  if (t.W > 65535 || t.H > 65535) return fail(DVS_ERR_UNSUPPORTED, "W, H must fit uint16");
+  if ((long long)t.tile_rows * t.W > kMaxTilePx) return fail(DVS_ERR_UNSUPPORTED, "tile_rows * W > 32768");
+  A.S = t.S; A.H = t.H; A.W = t.W; A.tile_rows = t.tile_rows;
+  A.tiles_per_stream = (t.H + t.tile_rows - 1) / t.tile_rows;
+  A.tile_px = t.tile_rows * t.W;
+  A.C = 2 + 2 * (enc_mode == DVS_ENC_NONE ? 0 : n_slots_or_none);
+  return DVS_OK;
+}
+
+int dvs_step_fused(const dvs_step_params *p, void *stream) {
+  if (!p || !p->curr || !p->ref || !p->records || !p->tile_counts) return fail(DVS_ERR_INVALID_ARGUMENT, "null pointer");
+  if (p->adaptive && !p->thr) return fail(DVS_ERR_INVALID_ARGUMENT, "adaptive mode needs a threshold plane");
+  if (p->update_mode < 0 || p->update_mode > DVS_UPD_NONE) return fail(DVS_ERR_INVALID_ARGUMENT, "update mode");
+  if (p->update_mode == DVS_UPD_RATE_ADPT && !p->adaptive) return fail(DVS_ERR_INVALID_ARGUMENT, "rate_adpt needs adaptive");
+  if ((p->update_mode == DVS_UPD_TIME_BIN_RAW || p->update_mode == DVS_UPD_TIME_BIN_THR) &&
+      (!p->enc.lut || p->enc.lut_len <= 0))
+    return fail(DVS_ERR_INVALID_ARGUMENT, "time-binary update needs a log2 table");
+  int rc = check_enc(&p->enc);
+  if (rc) return rc;
+  TileArgs A;
+  memset(&A, 0, sizeof(A));
+  rc = fill_tiling(A, p->tiling, p->enc.n_slots, p->enc.mode);
+  if (rc) return rc;
+  const int k = p->inh_k > 1 ? p->inh_k : 1;
+  if (k > 1 && (A.W % k || A.H % k || A.tile_rows % k))
+    return fail(DVS_ERR_INVALID_ARGUMENT, "inhibition needs W, H and tile_rows divisible by inh_k (reference: IndexError)");
+  A.adaptive = p->adaptive; A.polarity = p->polarity; A.uncoded = p->uncoded; A.inh_k = k;
+  A.thr_scalar = p->threshold;
+  A.upd.mode = p->update_mode; A.upd.uncoded = p->uncoded; A.upd.threshold = p->threshold;
+  A.upd.min_thr = p->min_thr; A.upd.max_thr = p->max_thr; A.upd.thr_down = p->thr_down; A.upd.thr_up = p->thr_up;
+  A.upd.max_time_ms = p->max_time_ms; A.upd.lut = p->enc.lut; A.upd.lut_len = p->enc.lut_len;
+  A.upd.hw = p->history_weight; A.upd.hw_is_one = p->history_weight == 1.0; A.upd.div_thr = make_div(p->threshold);
+  A.enc = make_enc(&p->enc);
+  A.fast_hist = (A.enc.mode == DVS_ENC_RATE || A.enc.mode == DVS_ENC_TIME) && A.enc.n_slots <= 8;
+  A.curr = p->curr; A.ref = p->ref; A.thr = p->thr;
+  A.diff_out = p->diff_out; A.abs_out = p->abs_diff_out; A.spk_out = p->spikes_out;
+  A.records = p->records; A.tile_counts = p->tile_counts; A.status = p->status;
+  const bool u8 = p->frame_dtype == DVS_FRAME_U8;
+  const long long P = (long long)A.H * A.W;
+  A.vec_ok = (P % 8 == 0) && (A.tile_px % 8 == 0) && aligned16(p->ref) && (!p->thr || aligned16(p->thr)) &&
+             (u8 ? ((reinterpret_cast<uintptr_t>(p->curr) & 7) == 0) : aligned16(p->curr)) &&
+             (!p->diff_out || aligned16(p->diff_out)) && (!p->abs_diff_out || aligned16(p->abs_diff_out)) &&
+             (!p->spikes_out || aligned16(p->spikes_out));
+  cudaStream_t st = as_stream(stream);
+  if (u8) return p->adaptive ? launch_tile_pass_u8_adpt(A, st) : launch_tile_pass_u8(A, st);
+  return p->adaptive ? launch_tile_pass_i16_adpt(A, st) : launch_tile_pass_i16(A, st);
+}
+
+int dvs_split_tiles(const dvs_tiling *tiling, const int16_t *spikes, const int16_t *abs_diff, int32_t polarity,
+                    const dvs_enc_params *enc, dvs_record *records, uint32_t *tile_counts, int32_t *global_max,
+                    int32_t *status, void *stream) {
+  if (!tiling || !spikes || !abs_diff || !records || !tile_counts) return fail(DVS_ERR_INVALID_ARGUMENT, "null pointer");
+  int rc = check_enc(enc);
+  if (rc) return rc;
+  TileArgs A;
+  memset(&A, 0, sizeof(A));
+  A.enc = make_enc(enc);
+  rc = fill_tiling(A, *tiling, A.enc.n_slots, A.enc.mode);
+  if (rc) return rc;
+  A.polarity = polarity; A.uncoded = enc ? enc->uncoded : 0; A.inh_k = 1;
+  A.upd.mode = DVS_UPD_NONE;
+  A.fast_hist = (A.enc.mode == DVS_ENC_RATE || A.enc.mode == DVS_ENC_TIME) && A.enc.n_slots <= 8;
+  A.curr = spikes; A.abs_in = abs_diff; A.records = records; A.tile_counts = tile_counts;
+  A.status = status; A.global_max = global_max;
+  const long long P = (long long)A.H * A.W;
+  A.vec_ok = (P % 8 == 0) && (A.tile_px % 8 == 0) && aligned16(spikes) && aligned16(abs_diff);
+  return launch_tile_pass_planes(A, as_stream(stream));
+}
+
+int dvs_lists_to_tiles(const int16_t *pos, int64_t n_pos, int64_t pos_stride, const int16_t *neg, int64_t n_neg,
+                       int64_t neg_stride, int32_t chunk, const dvs_enc_params *enc, dvs_record *records,
+                       uint32_t *tile_counts, int32_t *status, void *stream) {
+  if (!enc || !records || !tile_counts || chunk <= 0 || chunk > kMaxTilePx || n_pos < 0 || n_neg < 0)
+    return fail(DVS_ERR_INVALID_ARGUMENT, "lists_to_tiles arguments");
+  if ((n_pos > 0 && !pos) || (n_neg > 0 && !neg)) return fail(DVS_ERR_INVALID_ARGUMENT, "null list");
+  int rc = check_enc(enc);
+  if (rc) return rc;
+  ListArgs A;
+  memset(&A, 0, sizeof(A));
+  A.pos = pos; A.neg = neg; A.n_pos = n_pos; A.n_neg = n_neg; A.pos_stride = pos_stride; A.neg_stride = neg_stride;
+  A.chunk = chunk;
+  A.n_pos_tiles = (int)((n_pos + chunk - 1) / chunk);
+  const int n_neg_tiles = (int)((n_neg + chunk - 1) / chunk);
+  A.tiles = A.n_pos_tiles + n_neg_tiles;
+  if (A.tiles == 0) A.tiles = 1;  // one empty tile keeps the scan / expand shapes valid
+  A.enc = make_enc(enc);
+  A.C = 2 + 2 * A.enc.n_slots;
+  A.records = records; A.tile_counts = tile_counts; A.status = status;
+  const size_t smem = (size_t)(A.enc.n_slots + 1) * sizeof(uint32_t);
+  k_lists_to_tiles<<<A.tiles, 256, smem, as_stream(stream)>>>(A);
+  return check_launch("k_lists_to_tiles");
+}
+
+int dvs_scan_tiles(int32_t S, int32_t tiles_per_stream, int32_t n_slots, const uint32_t *tile_counts,
+                   uint32_t *tile_excl, uint32_t *stream_totals, int64_t *seg_offsets, void *stream) {
+  if (S <= 0 || tiles_per_stream <= 0 || n_slots < 0 || n_slots > kMaxSlots || !tile_counts || !tile_excl ||
+      !stream_totals)
+    return fail(DVS_ERR_INVALID_ARGUMENT, "scan_tiles arguments");
+  const int C = 2 + 2 * n_slots;
+  const long long n_rows = (long long)S * C;
+  if (n_rows > 0x7fffffffll / 32) return fail(DVS_ERR_UNSUPPORTED, "S * C too large");
+  const unsigned grid = (unsigned)((n_rows * 32 + 255) / 256);
+  k_scan_tiles<<<grid, 256, 0, as_stream(stream)>>>((int)n_rows, tiles_per_stream, tile_counts, tile_excl, stream_totals);
+  int rc = check_launch("k_scan_tiles");
+  if (rc) return rc;
+  if (seg_offsets) {
+    if (n_slots == 0) {
+      cudaError_t e = cudaMemsetAsync(seg_offsets, 0, sizeof(int64_t), as_stream(stream));
+      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+      return DVS_OK;
+    }
+    k_scan_segments<<<1, 1024, 0, as_stream(stream)>>>(S, n_slots, stream_totals,
+                                                       reinterpret_cast<long long *>(seg_offsets));
+    rc = check_launch("k_scan_segments");
+  }
+  return rc;
+}
+
+int dvs_aer_expand(int32_t S, int32_t tiles_per_stream, int32_t tile_px, const dvs_enc_params *enc,
+                   const dvs_record *records, const uint32_t *tile_counts, const uint32_t *tile_excl,
+                   const int64_t *seg_offsets, dvs_event *events, int64_t event_cap, int32_t *status, void *stream) {
+  if (S <= 0 || tiles_per_stream <= 0 || tile_px <= 0 || !enc || enc->mode == DVS_ENC_NONE || !records ||
+      !tile_counts || !tile_excl || !seg_offsets || (!events && event_cap > 0))
+    return fail(DVS_ERR_INVALID_ARGUMENT, "aer_expand arguments");
+  int rc = check_enc(enc);
+  if (rc) return rc;
+  ExpandArgs A;
+  memset(&A, 0, sizeof(A));
+  A.S = S; A.tps = tiles_per_stream; A.tile_px = tile_px; A.enc = make_enc(enc); A.C = 2 + 2 * A.enc.n_slots;
+  A.records = records; A.tile_counts = tile_counts; A.tile_excl = tile_excl;
+  A.seg_offsets = reinterpret_cast<const long long *>(seg_offsets);
+  A.events = events; A.event_cap = event_cap; A.status = status;
+  const long long n_tasks = 2ll * S * tiles_per_stream;
+  long long grid = (n_tasks + 7) / 8;
+  const long long cap = 148ll * 32;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  k_expand<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(A);
+  return check_launch("k_expand");
+}
+
+int dvs_gather_split(int32_t s, int32_t tiles_per_stream, int32_t tile_px, int32_t n_slots, const dvs_record *records,
+                     const uint32_t *tile_counts, const uint32_t *tile_excl, int16_t *pos_out, int64_t pos_stride,
+                     int16_t *neg_out, int64_t neg_stride, void *stream) {
+  if (s < 0 || tiles_per_stream <= 0 || tile_px <= 0 || !records || !tile_counts || !tile_excl)
+    return fail(DVS_ERR_INVALID_ARGUMENT, "gather_split arguments");
+  const int C = 2 + 2 * n_slots;
+  long long grid = (2ll * tiles_per_stream + 7) / 8;
+  if (grid > 148ll * 16) grid = 148ll * 16;
+  k_gather_split<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(s, tiles_per_stream, tile_px, C, records, tile_counts,
+                                                                tile_excl, pos_out, pos_stride, neg_out, neg_stride);
+  return check_launch("k_gather_split");
+}
+
+int dvs_thresholded_difference_i16(const int16_t *curr, const int16_t *ref, const int16_t *thr_plane, int32_t thr_scalar,
+                                   int16_t *diff, int16_t *abs_diff, int16_t *spikes, int64_t n_px, void *stream) {
+  if (!curr || !ref || !diff || !abs_diff || !spikes || n_px < 0) return fail(DVS_ERR_INVALID_ARGUMENT, "null pointer");
+  if (n_px == 0) return DVS_OK;
+  const int vec = aligned16(curr) && aligned16(ref) && aligned16(diff) && aligned16(abs_diff) && aligned16(spikes) &&
+                  (!thr_plane || aligned16(thr_plane));
+  const long long groups = (n_px + 7) / 8;
+  k_thresholded_difference<<<(unsigned)((groups + 255) / 256), 256, 0, as_stream(stream)>>>(
+      curr, ref, thr_plane, thr_scalar, diff, abs_diff, spikes, n_px, vec);
+  return check_launch("k_thresholded_difference");
+}
+
+int dvs_local_inhibition_i16(int16_t *spikes, const int16_t *abs_diff, int32_t S, int32_t H, int32_t W, int32_t k,
+                             void *stream) {
+  if (!spikes || !abs_diff || S <= 0 || H <= 0 || W <= 0 || k <= 0) return fail(DVS_ERR_INVALID_ARGUMENT, "inhibition arguments");
+  if (W % k || H % k) return fail(DVS_ERR_INVALID_ARGUMENT, "inhibition needs W and H divisible by inh_width (reference: IndexError)");
+  if (k == 1) return DVS_OK;
+  const long long n_areas = (long long)S * (W / k) * (H / k);
+  k_local_inhibition<<<(unsigned)((n_areas + 255) / 256), 256, 0, as_stream(stream)>>>(spikes, abs_diff, S, H, W, k);
+  return check_launch("k_local_inhibition");
+}
+
+int dvs_update_reference_i16(int32_t mode, int32_t uncoded, const int16_t *abs_diff, const int16_t *spikes,
+                             const int16_t *ref_in, int16_t *ref_out, int16_t *thr, int16_t *thr_out, int32_t threshold,
+                             int32_t min_thr, int32_t max_thr, int32_t thr_down, int32_t thr_up, int32_t max_time_ms,
+                             double history_weight, const uint8_t *lut, int32_t lut_len, int64_t n_px, int32_t *status,
+                             void *stream) {
+  if (!abs_diff || !spikes || !ref_in || !ref_out || n_px < 0) return fail(DVS_ERR_INVALID_ARGUMENT, "null pointer");
+  if (mode < 0 || mode >= DVS_UPD_NONE) return fail(DVS_ERR_INVALID_ARGUMENT, "update mode");
+  if (mode == DVS_UPD_RATE_ADPT && (!thr || !thr_out)) return fail(DVS_ERR_INVALID_ARGUMENT, "rate_adpt needs threshold planes");
+  if ((mode == DVS_UPD_TIME_BIN_RAW || mode == DVS_UPD_TIME_BIN_THR) && (!lut || lut_len <= 0))
+    return fail(DVS_ERR_INVALID_ARGUMENT, "time-binary update needs a log2 table");
+  if (n_px == 0) return DVS_OK;
+  UpdateArgs U;
+  memset(&U, 0, sizeof(U));
+  U.mode = mode; U.uncoded = uncoded; U.threshold = threshold; U.min_thr = min_thr; U.max_thr = max_thr;
+  U.thr_down = thr_down; U.thr_up = thr_up; U.max_time_ms = max_time_ms; U.lut = lut; U.lut_len = lut_len;
+  U.hw = history_weight; U.hw_is_one = history_weight == 1.0; U.div_thr = make_div(threshold);
+  const int vec = aligned16(abs_diff) && aligned16(spikes) && aligned16(ref_in) && aligned16(ref_out) &&
+                  (!thr || aligned16(thr)) && (!thr_out || aligned16(thr_out));
+  const long long groups = (n_px + 7) / 8;
+  k_update_reference<<<(unsigned)((groups + 255) / 256), 256, 0, as_stream(stream)>>>(U, abs_diff, spikes, ref_in, ref_out,
+                                                                                     thr, thr_out, n_px, vec, status);
+  return check_launch("k_update_reference");
+}
+
+int dvs_update_reference_noise_i16(int32_t thresh_variant, const int16_t *abs_diff, const int16_t *spikes,
+                                   const int16_t *ref_in, int16_t *ref_out, int32_t W, int32_t H, int32_t threshold,
+                                   int32_t max_time_ms, double history_weight, const uint8_t *lut, int32_t lut_len,
+                                   const int16_t *sample, int64_t n_sample, uint8_t *flags, int32_t *status, void *stream) {
+  if (!abs_diff || !spikes || !ref_in || !ref_out || !flags || W <= 0 || H <= 0 || n_sample < 0 || (n_sample > 0 && !sample))
+    return fail(DVS_ERR_INVALID_ARGUMENT, "noise update arguments");
+  if (!thresh_variant && (!lut || lut_len <= 0)) return fail(DVS_ERR_INVALID_ARGUMENT, "raw noise update needs a log2 table");
+  const long long n = (long long)W * H;
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)n, st);
+  if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+  if (n_sample > 0) {
+    k_mark_samples<<<(unsigned)((n_sample + 255) / 256), 256, 0, st>>>(sample, n_sample, W, H, flags, status);
+    int rc = check_launch("k_mark_samples");
+    if (rc) return rc;
+  }
+  k_update_noise<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(thresh_variant, abs_diff, spikes, ref_in, ref_out, n,
+                                                             make_div(threshold), max_time_ms, history_weight,
+                                                             history_weight == 1.0, lut, lut_len, flags, status);
+  return check_launch("k_update_noise");
+}
+
+int dvs_step_f32(const float *src, float *diff, float *ref, float *thr, float relax, float up, float down, int64_t n_px,
+                 void *stream) {
+  if (!src || !ref || !thr || n_px < 0) return fail(DVS_ERR_INVALID_ARGUMENT, "null pointer");
+  if (n_px == 0) return DVS_OK;
+  const int vec = aligned16(src) && aligned16(ref) && aligned16(thr) && (!diff || aligned16(diff));
+  const long long groups = (n_px + 3) / 4;
+  k_step_f32<<<(unsigned)((groups + 255) / 256), 256, 0, as_stream(stream)>>>(src, diff, ref, thr, relax, up, down, n_px, vec);
+  return check_launch("k_step_f32");
+}
+
+int dvs_keys_from_events(const dvs_event *events, int64_t n, int32_t uncoded, int32_t flag_shift, int32_t data_shift,
+                         int32_t data_mask, int16_t *keys, void *stream) {
+  if (n < 0 || (n > 0 && (!events || !keys))) return fail(DVS_ERR_INVALID_ARGUMENT, "keys_from_events arguments");
+  if (n == 0) return DVS_OK;
+  k_keys_from_events<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(events, n, uncoded, flag_shift, data_shift,
+                                                                                data_mask, keys);
+  return check_launch("k_keys_from_events");
+}
+
+}  // extern "C"

@@ -1,0 +1,300 @@
+"""``DVSStreams`` -- the batched, state-resident form of the spike-generation path.
+
+One object owns the reference (and adaptive-threshold) planes of ``S`` independent camera streams in
+HBM and advances all of them by one frame per ``step()`` with three launches on the current CUDA
+stream (fused tile pass -> scans -> AER expand; ``include/pydvs_b200.h``).  It is the native
+counterpart of the loop every reference caller writes by hand
+(``stand_alone.py:160-185``, ``external_dvs_emulator_device.py:549-683``):
+
+    thresholded_difference[_adpt] -> local_inhibition -> update_reference_* -> split_spikes
+    -> make_spike_lists_*
+
+and of the C++ ``PyDVS`` object that owns ``_ref/_thr`` (``pydvs/cpp/dvs_emu.hpp:89-108``).
+PyTorch is used for device memory and streams only.
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check
+from .spike_lists import SpikeLists
+
+UP_POLARITY, DOWN_POLARITY, MERGED_POLARITY, RECTIFIED_POLARITY = 0, 1, 2, 3
+OUTPUT_RATE, OUTPUT_TIME, OUTPUT_TIME_BIN, OUTPUT_TIME_BIN_THR = "RATE", "TIME", "TIME_BIN", "TIME_BIN_THR"
+
+_ENC = {OUTPUT_RATE: _lib.ENC_RATE, OUTPUT_TIME: _lib.ENC_TIME, OUTPUT_TIME_BIN: _lib.ENC_TIME_BIN,
+        OUTPUT_TIME_BIN_THR: _lib.ENC_TIME_BIN_THR}
+# reference-update rule per output type, external_dvs_emulator_device.py:594-632
+_UPD = {OUTPUT_RATE: _lib.UPD_RATE, OUTPUT_TIME: _lib.UPD_RATE, OUTPUT_TIME_BIN: _lib.UPD_TIME_BIN_RAW,
+        OUTPUT_TIME_BIN_THR: _lib.UPD_TIME_BIN_THR}
+
+
+def current_stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+@dataclass
+class DVSConfig:
+    """Mirrors the constructor arguments of ``ExternalDvsEmulatorDevice``
+    (``external_dvs_emulator_device.py:73-84``) plus the geometry / batching the CUDA path needs."""
+    width: int
+    height: int
+    streams: int = 1
+    output_type: str = OUTPUT_RATE
+    polarity: int = MERGED_POLARITY
+    threshold: int = 12
+    adaptive_threshold: bool = False
+    min_threshold: int = 6
+    max_threshold: int = 168
+    threshold_delta_down: int = 2
+    threshold_delta_up: int = 12
+    history_weight: float = 1.0
+    fps: Optional[float] = None
+    max_time_ms: Optional[int] = None          # int(1000 / fps) when None (stand_alone.py:138)
+    num_bins: Optional[int] = None             # 8 TIME_BIN, 6 TIME_BIN_THR, else max_time_ms
+    num_bits_per_spike: int = 4                # log2 table row = num_bits_per_spike - 1
+    log2_table: Optional[object] = None        # explicit uint8 LUT row overrides the generated one
+    inh_area_width: int = 0                    # <= 1: no local inhibition
+    uncoded: bool = False                      # rules of generate_spikes_uncoded.pyx
+    encoder_threshold: Optional[int] = None    # threshold given to make_spike_lists_*
+    ref0: int = 128                            # external_dvs_emulator_device.py:133
+    threshold0: Optional[int] = None           # initial adaptive threshold plane (device: zeros)
+    frame_dtype: str = "int16"                 # "int16" (API parity) or "uint8" (camera-native)
+    tile_rows: Optional[int] = None
+
+    def resolved(self):
+        c = DVSConfig(**self.__dict__)
+        if c.max_time_ms is None:
+            c.max_time_ms = int(1000.0 / c.fps) if c.fps else 8
+        if c.num_bins is None:  # external_dvs_emulator_device.py:167-172
+            c.num_bins = {OUTPUT_TIME_BIN: 8, OUTPUT_TIME_BIN_THR: 6}.get(c.output_type, c.max_time_ms)
+        if c.encoder_threshold is None:
+            c.encoder_threshold = c.min_threshold if c.adaptive_threshold else c.threshold
+        if c.output_type not in _ENC:
+            raise ValueError("unknown output_type %r" % (c.output_type,))
+        return c
+
+
+def log2_table_row(num_active_bits, bit_resolution):
+    """Row ``num_active_bits - 1`` of ``generate_log2_table`` (``generate_spikes.pyx:1105-1118``):
+    keep the top ``max(row, 1)`` set bits of every value in ``[0, 2**bit_resolution)``."""
+    from .generate_spikes import generate_log2_table
+    return generate_log2_table(num_active_bits, bit_resolution)[num_active_bits - 1]
+
+
+class StepResult:
+    """Device-resident AER output of one ``DVSStreams.step``.
+
+    ``events[seg_offsets[(s * n_slots + slot) * 2 + pol] : seg_offsets[... + 1]]`` are the events of
+    stream ``s``, time slot ``slot``, list ``pol`` (0 = pos, 1 = neg) in the reference's order
+    (SURVEY.md Appendix A.7).  Each event is 8 bytes: uint16 x, y, t and int16 p.
+    """
+
+    def __init__(self, owner, events, seg_offsets, status):
+        self._owner, self.events_raw, self.seg_offsets, self._status = owner, events, seg_offsets, status
+        self._off_host = None
+
+    # -- host-side accessors (synchronise) ----------------------------------------------------
+    def offsets_host(self):
+        if self._off_host is None:
+            self._off_host = self.seg_offsets.cpu().numpy()
+            self._owner.check_status()
+        return self._off_host
+
+    def total_events(self):
+        return int(self.offsets_host()[-1])
+
+    def events_per_stream(self):
+        o = self.offsets_host()
+        per = 2 * self._owner.n_slots
+        return np.diff(o[::per]) if per else np.zeros(self._owner.S, dtype=np.int64)
+
+    def events(self):
+        """int16 view [N, 4] of (x, y, t, p); x, y, t are uint16 bit patterns."""
+        n = self.total_events()
+        return self.events_raw[:n].view(torch.int16).view(-1, 4)
+
+    def keys(self, flag_shift, data_shift, data_mask, stream=None):
+        """The reference's int16 AER keys (``spike_to_key``) for all events or one stream's."""
+        o = self.offsets_host()
+        per = 2 * self._owner.n_slots
+        lo, hi = (0, int(o[-1])) if stream is None else (int(o[stream * per]), int(o[(stream + 1) * per]))
+        keys = torch.empty(max(hi - lo, 0), dtype=torch.int16, device=self.events_raw.device)
+        if hi > lo:
+            check(lib.dvs_keys_from_events(_ptr(self.events_raw[lo:hi]), hi - lo, int(self._owner.cfg.uncoded),
+                                           int(flag_shift), int(data_shift), int(data_mask), _ptr(keys),
+                                           current_stream_ptr()))
+        return keys
+
+    def spike_lists(self, stream, flag_shift, data_shift, data_mask):
+        """What ``make_spike_lists_*`` returns for one stream: a list of ``n_slots`` lists."""
+        o = self.offsets_host()
+        n_slots = self._owner.n_slots
+        per = 2 * n_slots
+        slot_off = o[stream * per:(stream + 1) * per + 1:2].copy()
+        cfg = self._owner.cfg
+        if cfg.uncoded and cfg.output_type in (OUTPUT_RATE, OUTPUT_TIME):
+            lo, hi = int(slot_off[0]), int(slot_off[-1])
+            ev = self.events_raw[lo:hi].view(torch.int16).view(-1, 4)
+            x = ev[:, 0].to(torch.int32) & 0xffff
+            y = ev[:, 1].to(torch.int32) & 0xffff
+            payload = torch.stack([y, x, ev[:, 3].to(torch.int32)], dim=1)
+        else:
+            payload = self.keys(flag_shift, data_shift, data_mask, stream=stream)
+        return SpikeLists(slot_off, payload)
+
+
+class DVSStreams:
+    def __init__(self, cfg: DVSConfig, device=None, event_capacity: Optional[int] = None,
+                 debug_planes: bool = False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pydvs_b200 needs a CUDA device (there is no CPU path)")
+        self.cfg = cfg = cfg.resolved()
+        self.device = torch.device(device if device is not None else "cuda")
+        self.S, self.H, self.W = cfg.streams, cfg.height, cfg.width
+        self.P = self.H * self.W
+        k = cfg.inh_area_width if cfg.inh_area_width and cfg.inh_area_width > 1 else 1
+        self.inh_k = k
+        if k > 1 and (self.W % k or self.H % k):
+            raise IndexError("local inhibition needs width and height divisible by inh_area_width")
+        self.enc_mode = _ENC[cfg.output_type]
+        self.upd_mode = _lib.UPD_RATE_ADPT if cfg.adaptive_threshold else _UPD[cfg.output_type]
+        self.n_slots = cfg.max_time_ms if cfg.output_type == OUTPUT_RATE else cfg.num_bins
+        if cfg.encoder_threshold == 0 and self.enc_mode != _lib.ENC_TIME_BIN:
+            raise ZeroDivisionError("integer division or modulo by zero")
+        with torch.cuda.device(self.device):
+            tr = cfg.tile_rows or lib.dvs_choose_tile_rows(self.S, self.H, self.W, k)
+        if tr <= 0:
+            raise NotImplementedError("frame too wide for one tile (width * inh_area_width > 32768)")
+        self.tile_rows = tr
+        self.tps = (self.H + tr - 1) // tr
+        self.tile_px = tr * self.W
+        self.C = 2 + 2 * self.n_slots
+        dev = self.device
+        # state
+        self.ref = torch.full((self.S, self.H, self.W), cfg.ref0, dtype=torch.int16, device=dev)
+        self.thr = None
+        if cfg.adaptive_threshold:
+            t0 = cfg.threshold if cfg.threshold0 is None else cfg.threshold0
+            self.thr = torch.full((self.S, self.H, self.W), t0, dtype=torch.int16, device=dev)
+        # LUT (time-binary modes)
+        self.lut = None
+        if self.enc_mode in (_lib.ENC_TIME_BIN, _lib.ENC_TIME_BIN_THR) or self.upd_mode in (
+                _lib.UPD_TIME_BIN_RAW, _lib.UPD_TIME_BIN_THR):
+            row = cfg.log2_table
+            if row is None:
+                row = log2_table_row(cfg.num_bits_per_spike, 8)
+            if isinstance(row, torch.Tensor):
+                row = row.detach().cpu().numpy()
+            self.lut = torch.from_numpy(np.ascontiguousarray(row, dtype=np.uint8)).to(dev)
+        # work buffers
+        n_tiles = self.S * self.tps
+        self.records = torch.empty(n_tiles * self.tile_px, dtype=torch.int64, device=dev)
+        self.tile_counts = torch.zeros(self.S * self.C * self.tps, dtype=torch.int32, device=dev)
+        self.tile_excl = torch.zeros_like(self.tile_counts)
+        self.stream_totals = torch.zeros(self.S * self.C, dtype=torch.int32, device=dev)
+        self.seg_offsets = torch.zeros(self.S * self.n_slots * 2 + 1, dtype=torch.int64, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        if event_capacity is None:
+            event_capacity = max(1024, (self.S * self.P) // 2)
+        self.event_capacity = int(event_capacity)
+        self.events = torch.empty(self.event_capacity, dtype=torch.int64, device=dev)
+        self.debug = None
+        if debug_planes:
+            self.debug = {n: torch.zeros((self.S, self.H, self.W), dtype=torch.int16, device=dev)
+                          for n in ("diff", "abs_diff", "spikes")}
+        self._enc = self._make_enc()
+        self._params = self._make_params()
+        self.frames_done = 0
+
+    # -- parameter blocks ---------------------------------------------------------------------
+    def _make_enc(self):
+        e = _lib.EncParams()
+        cfg = self.cfg
+        e.mode, e.uncoded, e.threshold, e.n_slots = self.enc_mode, int(cfg.uncoded), int(cfg.encoder_threshold), self.n_slots
+        e.u16_vals = int(cfg.uncoded and self.enc_mode in (_lib.ENC_RATE, _lib.ENC_TIME))
+        e.lut_len = int(self.lut.numel()) if self.lut is not None else 0
+        e.lut = self.lut.data_ptr() if self.lut is not None else None
+        return e
+
+    def _make_params(self):
+        cfg, p = self.cfg, _lib.StepParams()
+        p.tiling = _lib.Tiling(self.S, self.H, self.W, self.tile_rows)
+        p.frame_dtype = _lib.FRAME_U8 if cfg.frame_dtype == "uint8" else _lib.FRAME_I16
+        p.adaptive, p.update_mode, p.uncoded = int(cfg.adaptive_threshold), self.upd_mode, int(cfg.uncoded)
+        p.threshold, p.min_thr, p.max_thr = int(cfg.threshold), int(cfg.min_threshold), int(cfg.max_threshold)
+        p.thr_down, p.thr_up, p.max_time_ms = int(cfg.threshold_delta_down), int(cfg.threshold_delta_up), int(cfg.max_time_ms)
+        p.inh_k, p.polarity, p.history_weight = self.inh_k, int(cfg.polarity), float(cfg.history_weight)
+        p.enc = self._enc
+        p.ref = self.ref.data_ptr()
+        p.thr = self.thr.data_ptr() if self.thr is not None else None
+        if self.debug:
+            p.diff_out, p.abs_diff_out, p.spikes_out = (self.debug[n].data_ptr() for n in ("diff", "abs_diff", "spikes"))
+        p.records, p.tile_counts, p.status = self.records.data_ptr(), self.tile_counts.data_ptr(), self.status.data_ptr()
+        return p
+
+    # -- the hot path -------------------------------------------------------------------------
+    def step(self, frames: torch.Tensor, expand: bool = True) -> StepResult:
+        """Advance every stream by one frame.  ``frames``: CUDA tensor [S, H, W] (or [H, W] when
+        S == 1) of the configured frame dtype.  Asynchronous: three kernel launches, no host sync."""
+        want = torch.uint8 if self.cfg.frame_dtype == "uint8" else torch.int16
+        if frames.dtype != want or not frames.is_cuda:
+            raise ValueError("frames must be a CUDA tensor of dtype %s" % want)
+        if frames.numel() != self.S * self.P or not frames.is_contiguous():
+            raise ValueError("frames must be contiguous with shape [%d, %d, %d]" % (self.S, self.H, self.W))
+        st = current_stream_ptr()
+        self._params.curr = frames.data_ptr()
+        check(lib.dvs_step_fused(C.byref(self._params), st))
+        check(lib.dvs_scan_tiles(self.S, self.tps, self.n_slots, _ptr(self.tile_counts), _ptr(self.tile_excl),
+                                 _ptr(self.stream_totals), _ptr(self.seg_offsets), st))
+        if expand:
+            self.expand()
+        self.frames_done += 1
+        return StepResult(self, self.events, self.seg_offsets, self.status)
+
+    def expand(self):
+        check(lib.dvs_aer_expand(self.S, self.tps, self.tile_px, C.byref(self._enc), _ptr(self.records),
+                                 _ptr(self.tile_counts), _ptr(self.tile_excl), _ptr(self.seg_offsets),
+                                 _ptr(self.events), self.event_capacity, _ptr(self.status), current_stream_ptr()))
+
+    def grow_events(self, capacity):
+        """Re-allocate the event buffer and redo the expand of the last step (records are kept)."""
+        self.event_capacity = int(capacity)
+        self.events = torch.empty(self.event_capacity, dtype=torch.int64, device=self.device)
+        self.status.zero_()
+        self.expand()
+        return StepResult(self, self.events, self.seg_offsets, self.status)
+
+    def check_status(self):
+        """Synchronises; raises what the reference would have raised for data-dependent faults."""
+        st = int(self.status.item())
+        if st:
+            self.status.zero_()
+        if st & _lib.STATUS_EVENT_OVERFLOW:
+            raise OverflowError("event buffer too small: call grow_events(capacity)")
+        if st & (_lib.STATUS_LUT_INDEX | _lib.STATUS_INDEX):
+            raise IndexError("index out of range for the log2 table")
+        if st & _lib.STATUS_SLOT_RANGE:
+            raise IndexError("time slot outside the list of lists (undefined in the reference)")
+
+    # -- split_spikes view of the last step ---------------------------------------------------
+    def split_spikes(self, stream=0):
+        """(neg[3, Nn], pos[3, Np]) of the last step for one stream, as ``split_spikes`` returns
+        them (``generate_spikes.pyx:716-719``)."""
+        tot = self.stream_totals.view(self.S, self.C)[stream, :2].cpu().numpy()
+        n_pos, n_neg = int(tot[0]), int(tot[1])
+        pos = torch.empty((3, n_pos), dtype=torch.int16, device=self.device)
+        neg = torch.empty((3, n_neg), dtype=torch.int16, device=self.device)
+        check(lib.dvs_gather_split(stream, self.tps, self.tile_px, self.n_slots, _ptr(self.records),
+                                   _ptr(self.tile_counts), _ptr(self.tile_excl), _ptr(pos), max(n_pos, 1),
+                                   _ptr(neg), max(n_neg, 1), current_stream_ptr()))
+        return neg, pos

@@ -1,0 +1,177 @@
+"""GPU parity of the fused, batched pipeline (DVSStreams: K1 tile pass -> K2 scans -> K3 expand) against
+the CPU oracle's frame loop, over several frames so that state drift is caught.  Bit-exact: reference
+planes, threshold planes, intermediate planes and the AER lists (keys, order, slots)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ENC = {"RATE": 0, "TIME": 1, "TIME_BIN": 2, "TIME_BIN_THR": 3}
+
+
+def _key_params(W, H):
+    ds = int(np.ceil(np.log2(max(W, H, 2))))
+    return min(2 * ds, 15), ds, min((1 << ds) - 1, 255)
+
+
+def _run_case(S, H, W, *, output_type="RATE", frames=6, source="random", inh=0, adaptive=False, hw=1.0,
+              polarity=2, uncoded=False, frame_dtype="int16", threshold=12, max_time_ms=8, num_bins=None,
+              thr0=None, tile_rows=None, seed=0, lut_bits=(2, 6), ref0=128):
+    from oracle import oracle as orc
+    from pydvs_b200 import DVSConfig, DVSStreams, synth
+    import pydvs_b200.generate_spikes as gs
+
+    lut = gs.generate_log2_table(lut_bits[0], lut_bits[1])[lut_bits[0] - 1] if "BIN" in output_type else None
+    cfg = DVSConfig(width=W, height=H, streams=S, output_type=output_type, polarity=polarity, threshold=threshold,
+                    adaptive_threshold=adaptive, history_weight=hw, max_time_ms=max_time_ms, num_bins=num_bins,
+                    inh_area_width=inh, uncoded=uncoded, frame_dtype=frame_dtype, log2_table=lut,
+                    threshold0=thr0, tile_rows=tile_rows, ref0=ref0)
+    dvs = DVSStreams(cfg, debug_planes=True, event_capacity=S * H * W * max(8, max_time_ms))
+    rc = dvs.cfg
+    fs, ds, dm = _key_params(W, H)
+    pipes = [orc.Pipeline(W, H, mode=ENC[output_type], threshold=threshold, max_time_ms=rc.max_time_ms,
+                          num_bins=rc.num_bins, history_weight=hw, inh_k=inh, polarity=polarity, adaptive=adaptive,
+                          min_thr=rc.min_threshold, max_thr=rc.max_threshold, down=rc.threshold_delta_down,
+                          up=rc.threshold_delta_up, lut=lut, uncoded=uncoded, flag_shift=fs, data_shift=ds,
+                          data_mask=dm, ref0=ref0, thr0=thr0) for _ in range(S)]
+    O = orc.Oracle(uncoded)
+    for t in range(frames):
+        if source == "random":
+            f16 = synth.random_frames(S, H, W, t, seed=seed)
+        elif source == "bar":
+            f16 = synth.moving_bar(S, H, W, t, noise=6, seed=seed)
+        else:
+            f16 = synth.random_frames(S, H, W, t, seed=seed, lo=100, hi=160)
+        f_dev = f16.to(torch.uint8) if frame_dtype == "uint8" else f16
+        f_host = f16.cpu().numpy()
+        # oracle planes for this frame (before the oracle pipeline advances its state)
+        exp_planes = []
+        for s in range(S):
+            if adaptive:
+                d, a, sp = O.thresholded_difference_adpt(f_host[s], pipes[s].ref, pipes[s].thr, 0, 0)
+            else:
+                d, a, sp = O.thresholded_difference(f_host[s], pipes[s].ref, threshold)
+            if inh > 1:
+                O.local_inhibition(sp, a, None, W, H, inh)
+            exp_planes.append((d, a, sp))
+        res = dvs.step(f_dev)
+        torch.cuda.synchronize()
+        dvs.check_status()
+        ref_gpu = dvs.ref.cpu().numpy()
+        thr_gpu = dvs.thr.cpu().numpy() if adaptive else None
+        dbg = {k: v.cpu().numpy() for k, v in dvs.debug.items()}
+        total = 0
+        for s in range(S):
+            exp_lists = pipes[s].step(f_host[s])
+            d, a, sp = exp_planes[s]
+            assert np.array_equal(dbg["diff"][s], d), (t, s, "diff")
+            assert np.array_equal(dbg["abs_diff"][s], a), (t, s, "abs_diff")
+            assert np.array_equal(dbg["spikes"][s], sp), (t, s, "spikes")
+            assert np.array_equal(ref_gpu[s], pipes[s].ref), (t, s, "ref")
+            if adaptive:
+                assert np.array_equal(thr_gpu[s], pipes[s].thr), (t, s, "thr")
+            got = res.spike_lists(s, fs, ds, dm)
+            assert len(got) == len(exp_lists)
+            assert got == exp_lists, (t, s, "lists")
+            total += sum(len(x) for x in exp_lists)
+            if t == frames - 1:  # split_spikes view of the same step
+                neg, pos = dvs.split_spikes(s)
+                n_e, p_e, _ = O.split_spikes(sp, a, polarity)
+                assert np.array_equal(neg.cpu().numpy(), n_e.view(np.int16))
+                assert np.array_equal(pos.cpu().numpy(), p_e.view(np.int16))
+        assert res.total_events() == total
+        assert int(res.events_per_stream().sum()) == total
+    return dvs
+
+
+def test_cfg1_128_rate_bar():
+    # BASELINE config 1: 128x128, rate coded, static threshold 12, max_time_ms 8, hw 1.0, MERGED
+    _run_case(1, 128, 128, output_type="RATE", source="bar", frames=12)
+
+
+def test_cfg2_mnist_shape_time_bin_thr_adaptive():
+    # BASELINE config 2 shape: 32x32 streams, time_bin_thr (6 bins), adaptive thresholds, hw 0.99
+    _run_case(48, 32, 32, output_type="TIME_BIN_THR", adaptive=True, hw=0.99, frames=8, source="narrow", ref0=0,
+              num_bins=6, threshold=12, thr0=12)
+
+
+def test_cfg3_rate_inhibition():
+    # BASELINE config 3 (reduced height): rate + local inhibition k=2, moving bar and dense random
+    _run_case(1, 96, 640, output_type="RATE", inh=2, source="bar", frames=5)
+    _run_case(1, 96, 640, output_type="RATE", inh=2, source="random", frames=4)
+
+
+def test_cfg4_time_adaptive_multi_stream():
+    # BASELINE config 4 shape (reduced): time coding, num_bins = max_time_ms = 4, adaptive threshold
+    _run_case(5, 54, 96, output_type="TIME", adaptive=True, max_time_ms=4, num_bins=4, source="bar", frames=8,
+              thr0=12)
+
+
+def test_cfg5_full_pipeline_multi_stream():
+    # BASELINE config 5 shape (reduced): threshold -> inhibition -> update -> AER pack, rate coded
+    _run_case(4, 64, 480, output_type="RATE", inh=2, source="bar", frames=6)
+    _run_case(3, 32, 3840, output_type="RATE", inh=2, source="random", frames=3)  # 4K-wide rows, J=4 tiles
+
+
+@pytest.mark.parametrize("output_type", ["RATE", "TIME", "TIME_BIN", "TIME_BIN_THR"])
+@pytest.mark.parametrize("uncoded", [False, True])
+def test_all_encoders(output_type, uncoded):
+    nb = {"TIME_BIN": 8, "TIME_BIN_THR": 6}.get(output_type, 8)
+    _run_case(2, 24, 40, output_type=output_type, uncoded=uncoded, num_bins=nb, frames=4, source="narrow",
+              lut_bits=(3, 8) if output_type == "TIME_BIN" else (2, 6), threshold=5)
+
+
+@pytest.mark.parametrize("polarity", [0, 1, 2, 3])
+def test_polarities(polarity):
+    _run_case(2, 16, 32, polarity=polarity, frames=3)
+
+
+def test_history_weight_fp64():
+    for hw in (0.99, 0.29, 0.5):
+        _run_case(1, 16, 48, hw=hw, frames=5, source="narrow")
+
+
+def test_uint8_frames():
+    _run_case(3, 32, 64, frame_dtype="uint8", inh=2, frames=4)
+    _run_case(2, 30, 50, frame_dtype="uint8", frames=3)  # unaligned: scalar loads
+
+
+def test_unaligned_and_generic_inhibition():
+    _run_case(2, 33, 17, frames=4)                       # P % 8 != 0: scalar path, groups straddle rows
+    _run_case(2, 12, 18, inh=3, frames=4)                # generic k, W % 8 != 0
+    _run_case(2, 16, 48, inh=4, frames=4)                # generic k = 4
+    _run_case(1, 10, 14, inh=2, frames=4)                # k = 2 but W % 8 != 0 -> generic
+    _run_case(1, 40, 40, inh=5, frames=3)
+
+
+def test_many_slots_and_large_slot_counts():
+    _run_case(2, 16, 32, max_time_ms=33, frames=3, threshold=3)     # > 8 slots: shared-memory histogram
+    _run_case(1, 16, 32, output_type="TIME", num_bins=40, max_time_ms=40, frames=3, threshold=2)
+
+
+def test_wide_tile_variant():
+    # W * inh_k > 8192 pixels per tile -> the 1024-thread generic variant
+    _run_case(1, 8, 2064, inh=4, frames=3)
+    _run_case(1, 4, 8200, inh=0, frames=2)
+
+
+def test_explicit_tile_rows_and_single_tile_streams():
+    _run_case(3, 32, 32, tile_rows=32, frames=3)
+    _run_case(2, 64, 64, tile_rows=2, inh=2, frames=3)
+
+
+def test_event_overflow_is_recoverable():
+    from pydvs_b200 import DVSConfig, DVSStreams, synth
+    cfg = DVSConfig(width=64, height=32, streams=2, output_type="RATE")
+    small = DVSStreams(cfg, event_capacity=8)
+    big = DVSStreams(cfg, event_capacity=64 * 32 * 2 * 8)
+    f = synth.random_frames(2, 32, 64, 0, seed=1)
+    r_small, r_big = small.step(f), big.step(f)
+    with pytest.raises(OverflowError):
+        r_small.offsets_host()
+    n = r_big.total_events()
+    assert n > 8
+    r2 = small.grow_events(n)
+    assert r2.total_events() == n
+    assert torch.equal(r2.events(), r_big.events())
