@@ -131,6 +131,8 @@ typedef struct dvs_step_params {
   int32_t max_time_ms;
   int32_t inh_k;            /* local_inhibition area width; <= 1: off                         */
   int32_t polarity;         /* DVS_POL_*                                                      */
+  int32_t force_generic;    /* 1: never take the specialised fast kernel (testing / profiling) */
+  int32_t reserved0;
   double history_weight;
   dvs_enc_params enc;
   const void *curr;         /* [S][H][W] frames, int16 or uint8                               */

@@ -583,6 +583,12 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
              (!p->diff_out || aligned16(p->diff_out)) && (!p->abs_diff_out || aligned16(p->abs_diff_out)) &&
              (!p->spikes_out || aligned16(p->spikes_out));
   cudaStream_t st = as_stream(stream);
+  // fast path: static threshold, rate update, no history decay, vector-friendly geometry
+  const bool fast = !p->adaptive && p->update_mode == DVS_UPD_RATE && p->history_weight == 1.0 &&
+                    p->threshold >= 2 && p->threshold <= 32767 && p->max_time_ms >= 0 && A.vec_ok &&
+                    A.W % 8 == 0 && A.tile_px / 8 <= 1024 && k <= 2 && !p->diff_out && !p->abs_diff_out &&
+                    !p->spikes_out && !p->force_generic;
+  if (fast) return u8 ? launch_tile_fast_u8(A, st) : launch_tile_fast_i16(A, st);
   if (u8) return p->adaptive ? launch_tile_pass_u8_adpt(A, st) : launch_tile_pass_u8(A, st);
   return p->adaptive ? launch_tile_pass_i16_adpt(A, st) : launch_tile_pass_i16(A, st);
 }

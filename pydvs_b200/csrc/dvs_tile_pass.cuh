@@ -74,8 +74,137 @@ DEV int sgn_get(uint32_t bits, int p) {
 }
 DEV uint32_t sgn_code(int s) { return s > 0 ? 1u : (s < 0 ? 2u : 0u); }
 
-template <int SRC, int J, int BDMAX, bool ADAPT, int KI>
-__global__ void __launch_bounds__(BDMAX) k_tile_pass(const __grid_constant__ TileArgs A) {
+// ---- ordered compaction shared by the generic and the fast tile kernels ------------------------
+// posm/negm: 8-bit list-membership masks per group; a_pk: abs_diff of the group's pixels.
+// Block-wide exclusive scan in (group j, thread) order == row-major pixel order, records written to the
+// tile's region (pos list from the front, neg list ending at the back), per-slot event counts of the
+// tile accumulated in `hist`, then the per-tile counters written component-major.
+template <int J>
+DEV void tile_compact(const TileArgs &A, int tile, int s_idx, int t_idx, int row0, const uint32_t (&posm)[J],
+                      const uint32_t (&negm)[J], const uint32_t (&a_pk)[J][4], uint32_t *wtot, uint32_t *hist,
+                      uint32_t *misc, int nh, unsigned status) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+  uint32_t cnt[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) cnt[j] = __popc(posm[j]) | (__popc(negm[j]) << 16);
+  uint32_t incl[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    uint32_t x = cnt[j];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(kFull, x, o);
+      if (lane >= o) x += y;
+    }
+    incl[j] = x;
+    if (lane == 31) wtot[j * NW + warp] = x;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int n_ent = J * NW;  // <= 128
+    uint32_t carry = 0;
+    for (int e0 = 0; e0 < n_ent; e0 += 32) {
+      const int e = e0 + lane;
+      const uint32_t v = e < n_ent ? wtot[e] : 0;
+      uint32_t x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(kFull, x, o);
+        if (lane >= o) x += y;
+      }
+      if (e < n_ent) wtot[e] = carry + x - v;
+      carry += __shfl_sync(kFull, x, 31);
+    }
+    if (lane == 0) misc[0] = carry;  // tile totals: #pos | #neg << 16
+  }
+  __syncthreads();
+  const uint32_t totals = misc[0];
+  const int n_pos_tile = totals & 0xffff, n_neg_tile = totals >> 16;
+
+  if (totals != 0) {
+    const size_t region = (size_t)tile * A.tile_px;
+    dvs_record *pos_dst = A.records + region;
+    dvs_record *neg_dst = A.records + region + (A.tile_px - n_neg_tile);
+    const bool fast_hist = A.fast_hist != 0;
+    unsigned long long hp = 0, hn = 0;  // 8 x 8-bit register histograms (fast path)
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      if ((posm[j] | negm[j]) == 0) continue;
+      const int q0 = (j * (int)blockDim.x + tid) * 8;
+      const uint32_t excl = wtot[j * NW + warp] + incl[j] - cnt[j];
+      uint32_t op = excl & 0xffff, on = excl >> 16;
+      const int yq = q0 / A.W;
+      int y = row0 + yq, x = q0 - yq * A.W;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const bool tp = (posm[j] >> p) & 1u, tn = (negm[j] >> p) & 1u;
+        if (tp || tn) {
+          const int a = get16(a_pk[j], p);
+          const uint2 rec = make_uint2((uint32_t)y | ((uint32_t)x << 16), (uint32_t)(a & 0xffff));
+          if (tp) *reinterpret_cast<uint2 *>(pos_dst + op++) = rec;
+          else *reinterpret_cast<uint2 *>(neg_dst + on++) = rec;
+          if (A.enc.mode != DVS_ENC_NONE) {
+            const int desc = enc_desc(A.enc, a, tp, status);
+            if (fast_hist) {  // RATE / TIME with n_slots <= 8: desc in [-1, 8]
+              if (desc >= 0 && desc < 8) {
+                if (tp) hp += 1ull << (8 * desc); else hn += 1ull << (8 * desc);
+              }
+            } else if (A.enc.mode == DVS_ENC_RATE || A.enc.mode == DVS_ENC_TIME) {
+              if (desc >= 0) atomicAdd(&hist[(tp ? 0 : nh) + desc], 1u);
+            } else {
+              for (int jj = 0; jj < A.enc.n_slots; ++jj) {
+                unsigned inv;
+                const unsigned sm = bin_slotmask(A.enc, jj, inv);
+                if (desc & inv) status |= DVS_STATUS_SLOT_RANGE;
+                const int m = __popc((unsigned)desc & sm);
+                if (m) atomicAdd(&hist[(tp ? 0 : nh) + jj], (unsigned)m);
+              }
+            }
+          }
+        }
+        if (++x == A.W) { x = 0; ++y; }
+      }
+    }
+    if (A.enc.mode != DVS_ENC_NONE && fast_hist) {
+      // 16 bins (2 polarities x 8) as 8 words of two 16-bit fields; one redux.sync each
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const unsigned long long h = (w < 4) ? hp : hn;
+        const int b = (w & 3) * 2;
+        uint32_t v = (uint32_t)((h >> (8 * b)) & 0xff) | ((uint32_t)((h >> (8 * b + 8)) & 0xff) << 16);
+        v = __reduce_add_sync(kFull, v);
+        if (lane == 0 && v) {
+          const int base = (w < 4 ? 0 : nh) + b;
+          if (v & 0xffff) atomicAdd(&hist[base], v & 0xffff);
+          if ((v >> 16) && b + 1 < nh) atomicAdd(&hist[base + 1], v >> 16);
+        }
+      }
+    }
+  }
+  status = __reduce_or_sync(kFull, status);
+  if (status && lane == 0 && A.status) atomicOr(A.status, (int)status);
+
+  // ---- per-tile counters, component-major: tile_counts[s][c][t] ---------------------------------
+  __syncthreads();
+  for (int c = tid; c < A.C; c += blockDim.x) {
+    uint32_t v;
+    if (c == 0) v = n_pos_tile;
+    else if (c == 1) v = n_neg_tile;
+    else {
+      const int slot = (c - 2) >> 1, pol = (c - 2) & 1;
+      const uint32_t *h = hist + (pol ? nh : 0);
+      if (A.enc.mode == DVS_ENC_RATE) {  // slot j holds every pixel with k > j
+        v = 0;
+        for (int kk = slot + 1; kk <= A.enc.n_slots; ++kk) v += h[kk];
+      } else v = h[slot];
+    }
+    A.tile_counts[((size_t)s_idx * A.C + c) * A.tiles_per_stream + t_idx] = v;
+  }
+}
+
+// The generic tile pass: every mode, every geometry, exact int16 wrap semantics for arbitrary inputs.
+template <int SRC, int J, bool ADAPT, int KI>
+DEV void tile_body(const TileArgs &A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [a_sm: tile_px int16 (KI != 0)] [wtot: 128 u32] [hist: 2*(n_slots+1) u32] [misc: 8 u32]
   int16_t *a_sm = reinterpret_cast<int16_t *>(smem_raw);
@@ -206,12 +335,11 @@ __global__ void __launch_bounds__(BDMAX) k_tile_pass(const __grid_constant__ Til
   }
 
   // ---- phase C: reference / threshold update, list membership, counts -------------------------
-  uint32_t cnt[J];          // #pos | #neg << 16 per group
   uint32_t posm[J], negm[J];  // 8-bit membership masks
   int mx_pos = INT_MIN, mx_neg = INT_MIN;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
-    cnt[j] = 0; posm[j] = 0; negm[j] = 0;
+    posm[j] = 0; negm[j] = 0;
     if (nval[j] <= 0) continue;
     const int q0 = (j * (int)blockDim.x + tid) * 8;
     uint32_t rn_pk[4] = {0, 0, 0, 0}, tn_pk[4] = {0, 0, 0, 0}, s_pk[4] = {0, 0, 0, 0};
@@ -233,7 +361,6 @@ __global__ void __launch_bounds__(BDMAX) k_tile_pass(const __grid_constant__ Til
         if (tn) { negm[j] |= 1u << p; mx_neg = max(mx_neg, a); }
       }
     }
-    cnt[j] = __popc(posm[j]) | (__popc(negm[j]) << 16);
     if (SRC != SRC_PLANES) {
       if (A.upd.mode != DVS_UPD_NONE) store8_i16(A.ref, plane_off + q0, nval[j], vec, rn_pk);
       if (ADAPT && A.upd.mode == DVS_UPD_RATE_ADPT) store8_i16(A.thr, plane_off + q0, nval[j], vec, tn_pk);
@@ -241,101 +368,6 @@ __global__ void __launch_bounds__(BDMAX) k_tile_pass(const __grid_constant__ Til
     }
   }
 
-  // ---- ordered compaction: block-wide exclusive scan in (group j, thread) order ----------------
-  uint32_t incl[J];
-#pragma unroll
-  for (int j = 0; j < J; ++j) {
-    uint32_t x = cnt[j];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(kFull, x, o);
-      if (lane >= o) x += y;
-    }
-    incl[j] = x;
-    if (lane == 31) wtot[j * NW + warp] = x;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    const int n_ent = J * NW;  // <= 128
-    uint32_t carry = 0;
-    for (int e0 = 0; e0 < n_ent; e0 += 32) {
-      const int e = e0 + lane;
-      const uint32_t v = e < n_ent ? wtot[e] : 0;
-      uint32_t x = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(kFull, x, o);
-        if (lane >= o) x += y;
-      }
-      if (e < n_ent) wtot[e] = carry + x - v;
-      carry += __shfl_sync(kFull, x, 31);
-    }
-    if (lane == 0) misc[0] = carry;  // tile totals: #pos | #neg << 16
-  }
-  __syncthreads();
-  const uint32_t totals = misc[0];
-  const int n_pos_tile = totals & 0xffff, n_neg_tile = totals >> 16;
-
-  if (totals != 0) {
-    const size_t region = (size_t)tile * A.tile_px;
-    dvs_record *pos_dst = A.records + region;
-    dvs_record *neg_dst = A.records + region + (A.tile_px - n_neg_tile);
-    const bool fast_hist = A.fast_hist != 0;
-    unsigned long long hp = 0, hn = 0;  // 8 x 8-bit register histograms (fast path)
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      if ((posm[j] | negm[j]) == 0) continue;
-      const int q0 = (j * (int)blockDim.x + tid) * 8;
-      const uint32_t excl = wtot[j * NW + warp] + incl[j] - cnt[j];
-      uint32_t op = excl & 0xffff, on = excl >> 16;
-      const int yq = q0 / A.W;
-      int y = row0 + yq, x = q0 - yq * A.W;
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const bool tp = (posm[j] >> p) & 1u, tn = (negm[j] >> p) & 1u;
-        if (tp || tn) {
-          const int a = get16(a_pk[j], p);
-          const uint2 rec = make_uint2((uint32_t)y | ((uint32_t)x << 16), (uint32_t)(a & 0xffff));
-          if (tp) *reinterpret_cast<uint2 *>(pos_dst + op++) = rec;
-          else *reinterpret_cast<uint2 *>(neg_dst + on++) = rec;
-          if (A.enc.mode != DVS_ENC_NONE) {
-            const int desc = enc_desc(A.enc, a, tp, status);
-            if (fast_hist) {  // RATE / TIME with n_slots <= 8: desc in [-1, 8]
-              if (desc >= 0 && desc < 8) {
-                if (tp) hp += 1ull << (8 * desc); else hn += 1ull << (8 * desc);
-              }
-            } else if (A.enc.mode == DVS_ENC_RATE || A.enc.mode == DVS_ENC_TIME) {
-              if (desc >= 0) atomicAdd(&hist[(tp ? 0 : nh) + desc], 1u);
-            } else {
-              for (int jj = 0; jj < A.enc.n_slots; ++jj) {
-                unsigned inv;
-                const unsigned sm = bin_slotmask(A.enc, jj, inv);
-                if (desc & inv) status |= DVS_STATUS_SLOT_RANGE;
-                const int m = __popc((unsigned)desc & sm);
-                if (m) atomicAdd(&hist[(tp ? 0 : nh) + jj], (unsigned)m);
-              }
-            }
-          }
-        }
-        if (++x == A.W) { x = 0; ++y; }
-      }
-    }
-    if (A.enc.mode != DVS_ENC_NONE && fast_hist) {
-      // 16 bins (2 polarities x 8) as 8 words of two 16-bit fields; one redux.sync each
-#pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        const unsigned long long h = (w < 4) ? hp : hn;
-        const int b = (w & 3) * 2;
-        uint32_t v = (uint32_t)((h >> (8 * b)) & 0xff) | ((uint32_t)((h >> (8 * b + 8)) & 0xff) << 16);
-        v = __reduce_add_sync(kFull, v);
-        if (lane == 0 && v) {
-          const int base = (w < 4 ? 0 : nh) + b;
-          if (v & 0xffff) atomicAdd(&hist[base], v & 0xffff);
-          if ((v >> 16) && b + 1 < nh) atomicAdd(&hist[base + 1], v >> 16);
-        }
-      }
-    }
-  }
   if (SRC == SRC_PLANES && A.global_max) {
     mx_pos = __reduce_max_sync(kFull, mx_pos);
     mx_neg = __reduce_max_sync(kFull, mx_neg);
@@ -344,25 +376,12 @@ __global__ void __launch_bounds__(BDMAX) k_tile_pass(const __grid_constant__ Til
       if (mx_neg != INT_MIN) atomicMax(&A.global_max[2 * s_idx + 1], mx_neg);
     }
   }
-  status = __reduce_or_sync(kFull, status);
-  if (status && lane == 0 && A.status) atomicOr(A.status, (int)status);
+  tile_compact<J>(A, tile, s_idx, t_idx, row0, posm, negm, a_pk, wtot, hist, misc, nh, status);
+}
 
-  // ---- per-tile counters, component-major: tile_counts[s][c][t] ---------------------------------
-  __syncthreads();
-  for (int c = tid; c < A.C; c += blockDim.x) {
-    uint32_t v;
-    if (c == 0) v = n_pos_tile;
-    else if (c == 1) v = n_neg_tile;
-    else {
-      const int slot = (c - 2) >> 1, pol = (c - 2) & 1;
-      const uint32_t *h = hist + (pol ? nh : 0);
-      if (A.enc.mode == DVS_ENC_RATE) {  // slot j holds every pixel with k > j
-        v = 0;
-        for (int kk = slot + 1; kk <= A.enc.n_slots; ++kk) v += h[kk];
-      } else v = h[slot];
-    }
-    A.tile_counts[((size_t)s_idx * A.C + c) * A.tiles_per_stream + t_idx] = v;
-  }
+template <int SRC, int J, int BDMAX, bool ADAPT, int KI>
+__global__ void __launch_bounds__(BDMAX) k_tile_pass(const __grid_constant__ TileArgs A) {
+  tile_body<SRC, J, ADAPT, KI>(A);
 }
 
 
@@ -417,5 +436,8 @@ int launch_tile_pass_i16_adpt(const TileArgs &A, cudaStream_t st);
 int launch_tile_pass_u8(const TileArgs &A, cudaStream_t st);
 int launch_tile_pass_u8_adpt(const TileArgs &A, cudaStream_t st);
 int launch_tile_pass_planes(const TileArgs &A, cudaStream_t st);
+// fast path (dvs_tile_fast.cuh): static threshold, rate update, history_weight == 1
+int launch_tile_fast_i16(const TileArgs &A, cudaStream_t st);
+int launch_tile_fast_u8(const TileArgs &A, cudaStream_t st);
 
 }  // namespace dvs

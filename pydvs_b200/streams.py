@@ -155,7 +155,7 @@ class StepResult:
 
 class DVSStreams:
     def __init__(self, cfg: DVSConfig, device=None, event_capacity: Optional[int] = None,
-                 debug_planes: bool = False):
+                 debug_planes: bool = False, force_generic: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("pydvs_b200 needs a CUDA device (there is no CPU path)")
         self.cfg = cfg = cfg.resolved()
@@ -212,6 +212,7 @@ class DVSStreams:
         if debug_planes:
             self.debug = {n: torch.zeros((self.S, self.H, self.W), dtype=torch.int16, device=dev)
                           for n in ("diff", "abs_diff", "spikes")}
+        self.force_generic = bool(force_generic)
         self._enc = self._make_enc()
         self._params = self._make_params()
         self.frames_done = 0
@@ -234,6 +235,7 @@ class DVSStreams:
         p.threshold, p.min_thr, p.max_thr = int(cfg.threshold), int(cfg.min_threshold), int(cfg.max_threshold)
         p.thr_down, p.thr_up, p.max_time_ms = int(cfg.threshold_delta_down), int(cfg.threshold_delta_up), int(cfg.max_time_ms)
         p.inh_k, p.polarity, p.history_weight = self.inh_k, int(cfg.polarity), float(cfg.history_weight)
+        p.force_generic = int(self.force_generic)
         p.enc = self._enc
         p.ref = self.ref.data_ptr()
         p.thr = self.thr.data_ptr() if self.thr is not None else None
@@ -251,15 +253,23 @@ class DVSStreams:
             raise ValueError("frames must be a CUDA tensor of dtype %s" % want)
         if frames.numel() != self.S * self.P or not frames.is_contiguous():
             raise ValueError("frames must be contiguous with shape [%d, %d, %d]" % (self.S, self.H, self.W))
-        st = current_stream_ptr()
-        self._params.curr = frames.data_ptr()
-        check(lib.dvs_step_fused(C.byref(self._params), st))
-        check(lib.dvs_scan_tiles(self.S, self.tps, self.n_slots, _ptr(self.tile_counts), _ptr(self.tile_excl),
-                                 _ptr(self.stream_totals), _ptr(self.seg_offsets), st))
+        self.tile_pass(frames)
+        self.scan()
         if expand:
             self.expand()
         self.frames_done += 1
         return StepResult(self, self.events, self.seg_offsets, self.status)
+
+    # the three launches of a step, individually (bench.py times K1 on its own)
+    def tile_pass(self, frames):
+        """K1: fused threshold / inhibition / state update / record compaction / slot counts."""
+        self._params.curr = frames.data_ptr()
+        check(lib.dvs_step_fused(C.byref(self._params), current_stream_ptr()))
+
+    def scan(self):
+        """K2: per-tile counters -> exclusive prefixes and CSR row pointers (two small launches)."""
+        check(lib.dvs_scan_tiles(self.S, self.tps, self.n_slots, _ptr(self.tile_counts), _ptr(self.tile_excl),
+                                 _ptr(self.stream_totals), _ptr(self.seg_offsets), current_stream_ptr()))
 
     def expand(self):
         check(lib.dvs_aer_expand(self.S, self.tps, self.tile_px, C.byref(self._enc), _ptr(self.records),

@@ -6,13 +6,13 @@ import torch
 
 
 def moving_bar(S, H, W, t, device="cuda", bg=64, bar=200, bar_width=None, speed=None, noise=0, seed=0,
-               dtype=torch.int16):
+               dtype=torch.int16, stream_offset=0):
     """Vertical bar (value `bar`, width W/16) on background `bg`, moving W/64 px per frame with
-    wrap-around; stream s starts at phase (s * 37) % W; optional uniform noise in [-noise, noise]."""
+    wrap-around; stream s starts at phase ((s + stream_offset) * 37) % W; optional uniform noise in [-noise, noise]."""
     bw = bar_width if bar_width is not None else max(1, W // 16)
     sp = speed if speed is not None else max(1, W // 64)
     x = torch.arange(W, device=device).view(1, 1, W)
-    phase = (torch.arange(S, device=device) * 37) % W
+    phase = ((torch.arange(S, device=device) + stream_offset) * 37) % W
     x0 = ((phase + t * sp) % W).view(S, 1, 1)
     inside = ((x - x0) % W) < bw
     frame = torch.where(inside, torch.tensor(bar, device=device), torch.tensor(bg, device=device))

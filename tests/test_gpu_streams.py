@@ -17,7 +17,7 @@ def _key_params(W, H):
 
 def _run_case(S, H, W, *, output_type="RATE", frames=6, source="random", inh=0, adaptive=False, hw=1.0,
               polarity=2, uncoded=False, frame_dtype="int16", threshold=12, max_time_ms=8, num_bins=None,
-              thr0=None, tile_rows=None, seed=0, lut_bits=(2, 6), ref0=128):
+              thr0=None, tile_rows=None, seed=0, lut_bits=(2, 6), ref0=128, debug=True, force_generic=False):
     from oracle import oracle as orc
     from pydvs_b200 import DVSConfig, DVSStreams, synth
     import pydvs_b200.generate_spikes as gs
@@ -27,7 +27,8 @@ def _run_case(S, H, W, *, output_type="RATE", frames=6, source="random", inh=0, 
                     adaptive_threshold=adaptive, history_weight=hw, max_time_ms=max_time_ms, num_bins=num_bins,
                     inh_area_width=inh, uncoded=uncoded, frame_dtype=frame_dtype, log2_table=lut,
                     threshold0=thr0, tile_rows=tile_rows, ref0=ref0)
-    dvs = DVSStreams(cfg, debug_planes=True, event_capacity=S * H * W * max(8, max_time_ms))
+    dvs = DVSStreams(cfg, debug_planes=debug, event_capacity=S * H * W * max(8, max_time_ms),
+                     force_generic=force_generic)
     rc = dvs.cfg
     fs, ds, dm = _key_params(W, H)
     pipes = [orc.Pipeline(W, H, mode=ENC[output_type], threshold=threshold, max_time_ms=rc.max_time_ms,
@@ -41,6 +42,10 @@ def _run_case(S, H, W, *, output_type="RATE", frames=6, source="random", inh=0, 
             f16 = synth.random_frames(S, H, W, t, seed=seed)
         elif source == "bar":
             f16 = synth.moving_bar(S, H, W, t, noise=6, seed=seed)
+        elif source == "wide":  # outside [0, 255]: exercises int16 wrap-around and the fast kernel's fallback
+            f16 = synth.random_frames(S, H, W, t, seed=seed, lo=-20000, hi=20000)
+            if t % 2:
+                f16[:, H // 2:, :] = synth.random_frames(S, H, W, t, seed=seed + 1)[:, H // 2:, :]
         else:
             f16 = synth.random_frames(S, H, W, t, seed=seed, lo=100, hi=160)
         f_dev = f16.to(torch.uint8) if frame_dtype == "uint8" else f16
@@ -60,14 +65,15 @@ def _run_case(S, H, W, *, output_type="RATE", frames=6, source="random", inh=0, 
         dvs.check_status()
         ref_gpu = dvs.ref.cpu().numpy()
         thr_gpu = dvs.thr.cpu().numpy() if adaptive else None
-        dbg = {k: v.cpu().numpy() for k, v in dvs.debug.items()}
+        dbg = {k: v.cpu().numpy() for k, v in dvs.debug.items()} if debug else None
         total = 0
         for s in range(S):
             exp_lists = pipes[s].step(f_host[s])
             d, a, sp = exp_planes[s]
-            assert np.array_equal(dbg["diff"][s], d), (t, s, "diff")
-            assert np.array_equal(dbg["abs_diff"][s], a), (t, s, "abs_diff")
-            assert np.array_equal(dbg["spikes"][s], sp), (t, s, "spikes")
+            if debug:
+                assert np.array_equal(dbg["diff"][s], d), (t, s, "diff")
+                assert np.array_equal(dbg["abs_diff"][s], a), (t, s, "abs_diff")
+                assert np.array_equal(dbg["spikes"][s], sp), (t, s, "spikes")
             assert np.array_equal(ref_gpu[s], pipes[s].ref), (t, s, "ref")
             if adaptive:
                 assert np.array_equal(thr_gpu[s], pipes[s].thr), (t, s, "thr")
@@ -159,6 +165,46 @@ def test_wide_tile_variant():
 def test_explicit_tile_rows_and_single_tile_streams():
     _run_case(3, 32, 32, tile_rows=32, frames=3)
     _run_case(2, 64, 64, tile_rows=2, inh=2, frames=3)
+
+
+# ---- the specialised fast kernel (static threshold, rate update, hw == 1; no debug planes) -----------
+@pytest.mark.parametrize("source", ["bar", "random", "narrow"])
+@pytest.mark.parametrize("inh", [0, 2])
+def test_fast_kernel_4k_rows(source, inh):
+    _run_case(2, 8, 3840, output_type="RATE", inh=inh, source=source, frames=5, debug=False)       # J = 4
+    _run_case(3, 32, 128, output_type="RATE", inh=inh, source=source, frames=5, debug=False)       # J = 1
+
+
+def test_fast_kernel_matches_generic_kernel_events():
+    from pydvs_b200 import DVSConfig, DVSStreams, synth
+    cfg = DVSConfig(width=1920, height=64, streams=3, output_type="RATE", inh_area_width=2)
+    a, b = DVSStreams(cfg), DVSStreams(cfg, force_generic=True)
+    for t in range(6):
+        f = synth.moving_bar(3, 64, 1920, t, noise=10, seed=2) if t % 3 else synth.random_frames(3, 64, 1920, t)
+        ra, rb = a.step(f), b.step(f)
+        assert torch.equal(a.ref, b.ref)
+        assert torch.equal(ra.seg_offsets, rb.seg_offsets)
+        assert torch.equal(ra.events(), rb.events())
+
+
+def test_fast_kernel_variants():
+    _run_case(2, 16, 64, frame_dtype="uint8", inh=2, frames=4, debug=False)
+    _run_case(2, 16, 64, frame_dtype="uint8", inh=0, frames=4, debug=False, source="bar")
+    _run_case(1, 128, 128, source="bar", frames=10, debug=False)                         # BASELINE config 1
+    _run_case(2, 16, 64, output_type="TIME", num_bins=8, frames=4, debug=False)
+    _run_case(2, 16, 64, max_time_ms=33, threshold=3, frames=3, debug=False)             # > 8 slots
+    _run_case(2, 16, 64, uncoded=True, frames=3, debug=False)
+    for pol in (0, 1, 3):
+        _run_case(1, 16, 64, polarity=pol, frames=3, debug=False)
+    _run_case(1, 16, 64, threshold=2, max_time_ms=200, frames=3, debug=False)
+    _run_case(1, 16, 64, threshold=300, frames=2, debug=False)                           # nothing can spike
+
+
+def test_fast_kernel_falls_back_outside_8bit_range():
+    _run_case(2, 16, 256, source="wide", frames=4, debug=False)          # every tile takes the generic body
+    _run_case(2, 16, 256, source="wide", frames=4, debug=False, inh=2)
+    _run_case(1, 8, 64, ref0=-3000, frames=3, debug=False)               # reference state outside the range
+    _run_case(2, 16, 256, source="wide", frames=3, debug=True)           # and the generic kernel itself
 
 
 def test_event_overflow_is_recoverable():
