@@ -61,6 +61,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=3)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--settle", type=int, default=24,
+                    help="untimed steps before the warm-up: with inhibition only one pixel of each 2x2 area moves "
+                         "its reference per frame, so the dense start-up transient (ref0 = 128 vs background 64) "
+                         "takes ~16 frames to die out")
     return ap.parse_args()
 
 
@@ -333,7 +337,7 @@ def run_ours(args, wl, rank, local_rank, world):
 
     # ---- warm-up -----------------------------------------------------------------------------
     step_i = 0
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) + max(args.settle, 0)):
         dvs.step(ring[step_i % args.ring])
         step_i += 1
     torch.cuda.synchronize()
@@ -419,7 +423,7 @@ def run_ours(args, wl, rank, local_rank, world):
         "config": {"workload": args.workload, "width": W, "height": H, "streams_per_gpu": S,
                    "streams_total": total_streams, "coding": wl["output_type"], "inhibition": wl["inh"],
                    "adaptive_threshold": wl["adaptive"], "pattern": args.pattern, "frame_dtype": args.frame_dtype,
-                   "ring_frames": args.ring, "l2": "inputs larger than L2 (%.1f GB touched per step)" % (step_bytes / 1e9),
+                   "ring_frames": args.ring, "settle_steps": args.settle, "l2": "inputs larger than L2 (%.1f GB touched per step)" % (step_bytes / 1e9),
                    "events_last_step": events_last_step, "tile_rows": dvs.tile_rows},
         "roofline": {"bound": "hbm", "kernel": "k_tile_pass (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

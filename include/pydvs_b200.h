@@ -144,6 +144,8 @@ typedef struct dvs_step_params {
   dvs_record *records;      /* S * tiles_per_stream * tile_rows * W records (tile-local lists) */
   uint32_t *tile_counts;    /* [S][C][tiles_per_stream]                                       */
   int32_t *status;          /* device status word or NULL                                     */
+  int32_t *redo;            /* optional scratch, 1 + S * tiles_per_stream int32: enables the    */
+                            /*   specialised fast kernel (tiles it declines are listed here)    */
 } dvs_step_params;
 
 /* ---- library ---------------------------------------------------------------------------------- */

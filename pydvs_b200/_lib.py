@@ -44,7 +44,8 @@ class StepParams(C.Structure):
                 ("history_weight", C.c_double), ("enc", EncParams),
                 ("curr", C.c_void_p), ("ref", C.c_void_p), ("thr", C.c_void_p),
                 ("diff_out", C.c_void_p), ("abs_diff_out", C.c_void_p), ("spikes_out", C.c_void_p),
-                ("records", C.c_void_p), ("tile_counts", C.c_void_p), ("status", C.c_void_p)]
+                ("records", C.c_void_p), ("tile_counts", C.c_void_p), ("status", C.c_void_p),
+                ("redo", C.c_void_p)]
 
 
 _P, _I32, _I64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double

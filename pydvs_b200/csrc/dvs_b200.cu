@@ -544,6 +544,7 @@ static int fill_tiling(TileArgs &A, const dvs_tiling &t, int n_slots_or_none, in
   A.S = t.S; A.H = t.H; A.W = t.W; A.tile_rows = t.tile_rows;
   A.tiles_per_stream = (t.H + t.tile_rows - 1) / t.tile_rows;
   A.tile_px = t.tile_rows * t.W;
+  A.inv_w = t.W >= 2 ? (unsigned)((0x100000000ull + (unsigned)t.W - 1) / (unsigned)t.W) : 0u;
   A.C = 2 + 2 * (enc_mode == DVS_ENC_NONE ? 0 : n_slots_or_none);
   return DVS_OK;
 }
@@ -587,7 +588,8 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
   const bool fast = !p->adaptive && p->update_mode == DVS_UPD_RATE && p->history_weight == 1.0 &&
                     p->threshold >= 2 && p->threshold <= 32767 && p->max_time_ms >= 0 && A.vec_ok &&
                     A.W % 8 == 0 && A.tile_px / 8 <= 1024 && k <= 2 && !p->diff_out && !p->abs_diff_out &&
-                    !p->spikes_out && !p->force_generic;
+                    !p->spikes_out && !p->force_generic && p->redo;
+  A.redo = p->redo;
   if (fast) return u8 ? launch_tile_fast_u8(A, st) : launch_tile_fast_i16(A, st);
   if (u8) return p->adaptive ? launch_tile_pass_u8_adpt(A, st) : launch_tile_pass_u8(A, st);
   return p->adaptive ? launch_tile_pass_i16_adpt(A, st) : launch_tile_pass_i16(A, st);

@@ -17,6 +17,7 @@ struct TileArgs {
   int S, H, W, tile_rows, tiles_per_stream, tile_px, C;
   int adaptive, polarity, uncoded, inh_k, vec_ok, fast_hist;
   int thr_scalar;
+  unsigned inv_w;          // ceil(2^32 / W): q / W == umulhi(q, inv_w) for q < 32768
   UpdateArgs upd;
   EncArgs enc;
   const void *curr;        // frames (SRC_I16 / SRC_U8) or spikes plane (SRC_PLANES)
@@ -27,6 +28,7 @@ struct TileArgs {
   uint32_t *tile_counts;
   int32_t *status;
   int32_t *global_max;     // [S][2] (pos list, neg list), SRC_PLANES only; INT_MIN = empty
+  int32_t *redo;           // [1 + tiles]: tiles the fast kernel hands to the generic body
 };
 
 DEV uint4 ld16(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
@@ -74,6 +76,69 @@ DEV int sgn_get(uint32_t bits, int p) {
 }
 DEV uint32_t sgn_code(int s) { return s > 0 ? 1u : (s < 0 ? 2u : 0u); }
 
+// ---- per-tile slot histogram helpers --------------------------------------------------------------
+// One record's contribution to the tile's per-slot event counts.  fast_hist (RATE / TIME with
+// n_slots <= 8): 8-bit fields of two 64-bit registers per thread (callers add < 256 records per
+// thread between flushes); otherwise shared-memory atomics.
+DEV void hist_add(const TileArgs &A, uint32_t *hist, int nh, int a, bool tp, unsigned long long &hp,
+                  unsigned long long &hn, unsigned &status) {
+  if (A.enc.mode == DVS_ENC_NONE) return;
+  const int desc = enc_desc(A.enc, a, tp, status);
+  if (A.fast_hist) {  // desc in [-1, 8]
+    if (desc >= 0 && desc < 8) {
+      if (tp) hp += 1ull << (8 * desc); else hn += 1ull << (8 * desc);
+    }
+  } else if (A.enc.mode == DVS_ENC_RATE || A.enc.mode == DVS_ENC_TIME) {
+    if (desc >= 0) atomicAdd(&hist[(tp ? 0 : nh) + desc], 1u);
+  } else {
+    for (int jj = 0; jj < A.enc.n_slots; ++jj) {
+      unsigned inv;
+      const unsigned sm = bin_slotmask(A.enc, jj, inv);
+      if (desc & inv) status |= DVS_STATUS_SLOT_RANGE;
+      const int m = __popc((unsigned)desc & sm);
+      if (m) atomicAdd(&hist[(tp ? 0 : nh) + jj], (unsigned)m);
+    }
+  }
+}
+
+// Flush the register histograms (one redux.sync per pair of bins), publish the status bits and write
+// the tile's counters component-major: tile_counts[s][c][t].  Must be reached by every thread.
+DEV void tile_finish(const TileArgs &A, int s_idx, int t_idx, uint32_t *hist, int nh, int n_pos_tile,
+                     int n_neg_tile, unsigned long long hp, unsigned long long hn, unsigned status) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (A.enc.mode != DVS_ENC_NONE && A.fast_hist && (n_pos_tile | n_neg_tile)) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {  // 16 bins (2 polarities x 8) as 8 words of two 16-bit fields
+      const unsigned long long h = (w < 4) ? hp : hn;
+      const int b = (w & 3) * 2;
+      uint32_t v = (uint32_t)((h >> (8 * b)) & 0xff) | ((uint32_t)((h >> (8 * b + 8)) & 0xff) << 16);
+      v = __reduce_add_sync(kFull, v);
+      if (lane == 0 && v) {
+        const int base = (w < 4 ? 0 : nh) + b;
+        if (v & 0xffff) atomicAdd(&hist[base], v & 0xffff);
+        if ((v >> 16) && b + 1 < nh) atomicAdd(&hist[base + 1], v >> 16);
+      }
+    }
+  }
+  status = __reduce_or_sync(kFull, status);
+  if (status && lane == 0 && A.status) atomicOr(A.status, (int)status);
+  __syncthreads();
+  for (int c = tid; c < A.C; c += blockDim.x) {
+    uint32_t v;
+    if (c == 0) v = n_pos_tile;
+    else if (c == 1) v = n_neg_tile;
+    else {
+      const int slot = (c - 2) >> 1, pol = (c - 2) & 1;
+      const uint32_t *h = hist + (pol ? nh : 0);
+      if (A.enc.mode == DVS_ENC_RATE) {  // slot j holds every pixel with k > j
+        v = 0;
+        for (int kk = slot + 1; kk <= A.enc.n_slots; ++kk) v += h[kk];
+      } else v = h[slot];
+    }
+    A.tile_counts[((size_t)s_idx * A.C + c) * A.tiles_per_stream + t_idx] = v;
+  }
+}
+
 // ---- ordered compaction shared by the generic and the fast tile kernels ------------------------
 // posm/negm: 8-bit list-membership masks per group; a_pk: abs_diff of the group's pixels.
 // Block-wide exclusive scan in (group j, thread) order == row-major pixel order, records written to the
@@ -120,13 +185,12 @@ DEV void tile_compact(const TileArgs &A, int tile, int s_idx, int t_idx, int row
   __syncthreads();
   const uint32_t totals = misc[0];
   const int n_pos_tile = totals & 0xffff, n_neg_tile = totals >> 16;
+  unsigned long long hp = 0, hn = 0;  // 8 x 8-bit register histograms (fast_hist)
 
   if (totals != 0) {
     const size_t region = (size_t)tile * A.tile_px;
     dvs_record *pos_dst = A.records + region;
     dvs_record *neg_dst = A.records + region + (A.tile_px - n_neg_tile);
-    const bool fast_hist = A.fast_hist != 0;
-    unsigned long long hp = 0, hn = 0;  // 8 x 8-bit register histograms (fast path)
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       if ((posm[j] | negm[j]) == 0) continue;
@@ -143,68 +207,18 @@ DEV void tile_compact(const TileArgs &A, int tile, int s_idx, int t_idx, int row
           const uint2 rec = make_uint2((uint32_t)y | ((uint32_t)x << 16), (uint32_t)(a & 0xffff));
           if (tp) *reinterpret_cast<uint2 *>(pos_dst + op++) = rec;
           else *reinterpret_cast<uint2 *>(neg_dst + on++) = rec;
-          if (A.enc.mode != DVS_ENC_NONE) {
-            const int desc = enc_desc(A.enc, a, tp, status);
-            if (fast_hist) {  // RATE / TIME with n_slots <= 8: desc in [-1, 8]
-              if (desc >= 0 && desc < 8) {
-                if (tp) hp += 1ull << (8 * desc); else hn += 1ull << (8 * desc);
-              }
-            } else if (A.enc.mode == DVS_ENC_RATE || A.enc.mode == DVS_ENC_TIME) {
-              if (desc >= 0) atomicAdd(&hist[(tp ? 0 : nh) + desc], 1u);
-            } else {
-              for (int jj = 0; jj < A.enc.n_slots; ++jj) {
-                unsigned inv;
-                const unsigned sm = bin_slotmask(A.enc, jj, inv);
-                if (desc & inv) status |= DVS_STATUS_SLOT_RANGE;
-                const int m = __popc((unsigned)desc & sm);
-                if (m) atomicAdd(&hist[(tp ? 0 : nh) + jj], (unsigned)m);
-              }
-            }
-          }
+          hist_add(A, hist, nh, a, tp, hp, hn, status);
         }
         if (++x == A.W) { x = 0; ++y; }
       }
     }
-    if (A.enc.mode != DVS_ENC_NONE && fast_hist) {
-      // 16 bins (2 polarities x 8) as 8 words of two 16-bit fields; one redux.sync each
-#pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        const unsigned long long h = (w < 4) ? hp : hn;
-        const int b = (w & 3) * 2;
-        uint32_t v = (uint32_t)((h >> (8 * b)) & 0xff) | ((uint32_t)((h >> (8 * b + 8)) & 0xff) << 16);
-        v = __reduce_add_sync(kFull, v);
-        if (lane == 0 && v) {
-          const int base = (w < 4 ? 0 : nh) + b;
-          if (v & 0xffff) atomicAdd(&hist[base], v & 0xffff);
-          if ((v >> 16) && b + 1 < nh) atomicAdd(&hist[base + 1], v >> 16);
-        }
-      }
-    }
   }
-  status = __reduce_or_sync(kFull, status);
-  if (status && lane == 0 && A.status) atomicOr(A.status, (int)status);
-
-  // ---- per-tile counters, component-major: tile_counts[s][c][t] ---------------------------------
-  __syncthreads();
-  for (int c = tid; c < A.C; c += blockDim.x) {
-    uint32_t v;
-    if (c == 0) v = n_pos_tile;
-    else if (c == 1) v = n_neg_tile;
-    else {
-      const int slot = (c - 2) >> 1, pol = (c - 2) & 1;
-      const uint32_t *h = hist + (pol ? nh : 0);
-      if (A.enc.mode == DVS_ENC_RATE) {  // slot j holds every pixel with k > j
-        v = 0;
-        for (int kk = slot + 1; kk <= A.enc.n_slots; ++kk) v += h[kk];
-      } else v = h[slot];
-    }
-    A.tile_counts[((size_t)s_idx * A.C + c) * A.tiles_per_stream + t_idx] = v;
-  }
+  tile_finish(A, s_idx, t_idx, hist, nh, n_pos_tile, n_neg_tile, hp, hn, status);
 }
 
 // The generic tile pass: every mode, every geometry, exact int16 wrap semantics for arbitrary inputs.
 template <int SRC, int J, bool ADAPT, int KI>
-DEV void tile_body(const TileArgs &A) {
+DEV void tile_body(const TileArgs &A, const int tile) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [a_sm: tile_px int16 (KI != 0)] [wtot: 128 u32] [hist: 2*(n_slots+1) u32] [misc: 8 u32]
   int16_t *a_sm = reinterpret_cast<int16_t *>(smem_raw);
@@ -215,7 +229,6 @@ DEV void tile_body(const TileArgs &A) {
   uint32_t *misc = hist + 2 * nh;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
-  const int tile = blockIdx.x;
   const int s_idx = tile / A.tiles_per_stream, t_idx = tile - s_idx * A.tiles_per_stream;
   const int row0 = t_idx * A.tile_rows;
   const int rows = min(A.tile_rows, A.H - row0);
@@ -381,7 +394,18 @@ DEV void tile_body(const TileArgs &A) {
 
 template <int SRC, int J, int BDMAX, bool ADAPT, int KI>
 __global__ void __launch_bounds__(BDMAX) k_tile_pass(const __grid_constant__ TileArgs A) {
-  tile_body<SRC, J, ADAPT, KI>(A);
+  tile_body<SRC, J, ADAPT, KI>(A, blockIdx.x);
+}
+
+// Generic body over the tiles the fast kernel declined (pixels outside [0, 255]): A.redo[0] = count,
+// A.redo[1..] = tile indices.  Launched after every fast pass; normally finds count == 0.
+template <int SRC, int J, int KI>
+__global__ void __launch_bounds__(256) k_tile_redo(const __grid_constant__ TileArgs A) {
+  const int n = A.redo[0];
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    tile_body<SRC, J, false, KI>(A, A.redo[1 + i]);
+    __syncthreads();  // shared memory is reused by the next tile
+  }
 }
 
 

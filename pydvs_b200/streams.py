@@ -204,6 +204,7 @@ class DVSStreams:
         self.stream_totals = torch.zeros(self.S * self.C, dtype=torch.int32, device=dev)
         self.seg_offsets = torch.zeros(self.S * self.n_slots * 2 + 1, dtype=torch.int64, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.redo = torch.zeros(1 + n_tiles, dtype=torch.int32, device=dev)
         if event_capacity is None:
             event_capacity = max(1024, (self.S * self.P) // 2)
         self.event_capacity = int(event_capacity)
@@ -242,6 +243,7 @@ class DVSStreams:
         if self.debug:
             p.diff_out, p.abs_diff_out, p.spikes_out = (self.debug[n].data_ptr() for n in ("diff", "abs_diff", "spikes"))
         p.records, p.tile_counts, p.status = self.records.data_ptr(), self.tile_counts.data_ptr(), self.status.data_ptr()
+        p.redo = self.redo.data_ptr()
         return p
 
     # -- the hot path -------------------------------------------------------------------------
