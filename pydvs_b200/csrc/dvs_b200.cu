@@ -588,7 +588,7 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
   const bool fast = !p->adaptive && p->update_mode == DVS_UPD_RATE && p->history_weight == 1.0 &&
                     p->threshold >= 2 && p->threshold <= 32767 && p->max_time_ms >= 0 && A.vec_ok &&
                     A.W % 8 == 0 && A.tile_px / 8 <= 1024 && k <= 2 && !p->diff_out && !p->abs_diff_out &&
-                    !p->spikes_out && !p->force_generic && p->redo;
+                    !p->spikes_out && !p->force_generic && p->redo && A.S <= 65535;
   A.redo = p->redo;
   if (fast) return u8 ? launch_tile_fast_u8(A, st) : launch_tile_fast_i16(A, st);
   if (u8) return p->adaptive ? launch_tile_pass_u8_adpt(A, st) : launch_tile_pass_u8(A, st);

@@ -106,7 +106,7 @@ DEV void hist_add(const TileArgs &A, uint32_t *hist, int nh, int a, bool tp, uns
 DEV void tile_finish(const TileArgs &A, int s_idx, int t_idx, uint32_t *hist, int nh, int n_pos_tile,
                      int n_neg_tile, unsigned long long hp, unsigned long long hn, unsigned status) {
   const int tid = threadIdx.x, lane = tid & 31;
-  if (A.enc.mode != DVS_ENC_NONE && A.fast_hist && (n_pos_tile | n_neg_tile)) {
+  if (A.enc.mode != DVS_ENC_NONE && A.fast_hist && (n_pos_tile | n_neg_tile) && __any_sync(kFull, (hp | hn) != 0)) {
 #pragma unroll
     for (int w = 0; w < 8; ++w) {  // 16 bins (2 polarities x 8) as 8 words of two 16-bit fields
       const unsigned long long h = (w < 4) ? hp : hn;
