@@ -12,5 +12,6 @@ from .spike_lists import SpikeLists  # noqa: F401
 from .streams import (DVSConfig, DVSStreams, StepResult, OUTPUT_RATE, OUTPUT_TIME, OUTPUT_TIME_BIN,  # noqa: F401
                       OUTPUT_TIME_BIN_THR, UP_POLARITY, DOWN_POLARITY, MERGED_POLARITY, RECTIFIED_POLARITY)
 from .float_mode import DVSOperatorF32, dvs_op  # noqa: F401
+from . import sharding, synth  # noqa: F401
 
 __version__ = "0.1.0"

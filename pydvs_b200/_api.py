@@ -94,10 +94,10 @@ def _c_int(v, name, lo, hi, cname):
     """Scalar conversion with the OverflowError / TypeError behaviour of Cython's C integer args."""
     if isinstance(v, (torch.Tensor, np.ndarray)) and getattr(v, "ndim", 0) == 0:
         v = v.item()
-    if isinstance(v, (float, np.floating)):
+    if isinstance(v, (float, np.floating, str, bytes)) or v is None:
         raise TypeError("an integer is required")
     try:
-        iv = int(v)
+        iv = v.__index__() if hasattr(v, "__index__") else int(v)
     except (TypeError, ValueError):
         raise TypeError("an integer is required")
     if iv < lo or iv > hi:
