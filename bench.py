@@ -411,7 +411,9 @@ def run_ours(args, wl, rank, local_rank, world):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get(args.workload + ":" + args.pattern)
+            entry = json.load(fh).get(args.workload + ":" + args.pattern)
+            if entry and args.frame_dtype == "int16":
+                traffic = entry["bytes_per_px"] * S * P  # bytes per launch, like `achieved`'s numerator
     except Exception:
         pass
     step_bytes = k1_bytes + 8 * events_last_step

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libpydvs_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
-STAMP = os.path.join(OBJ_DIR, "sources.sha256")
+STAMP = LIB + ".sha256"  # next to the library: travels with it to the GPU box
 
 UNITS = ["dvs_b200.cu", "tile_pass_i16.cu", "tile_pass_i16_adpt.cu", "tile_pass_u8.cu",
          "tile_pass_u8_adpt.cu", "tile_pass_planes.cu", "tile_fast_i16.cu", "tile_fast_u8.cu"]
