@@ -521,6 +521,7 @@ int dvs_get_limits(dvs_limits *out) {
 int dvs_choose_tile_rows(int32_t S, int32_t H, int32_t W, int32_t inh_k) {
   const int k = inh_k > 1 ? inh_k : 1;
   if (S <= 0 || H <= 0 || W <= 0 || (long long)W * k > kMaxTilePx) return -1;
+  if (k == 2 && W >= 1024 && W % 8 == 0 && H % 2 == 0) return 2;  // 2x2 areas stay inside one thread (k_tile_fast2)
   const int target_px = 8192;
   int rows = (target_px / W) / k * k;
   if (rows < k) rows = k;

@@ -44,8 +44,9 @@ __global__ void __launch_bounds__(256, 4) k_tile_fast(const __grid_constant__ Ti
   const int tile = s_idx * A.tiles_per_stream + t_idx;
   const int row0 = t_idx * A.tile_rows;
   const int npx = min(A.tile_rows, A.H - row0) * A.W;  // multiple of 8 (host-checked)
-  const size_t plane_off = (size_t)s_idx * A.H * A.W + (size_t)row0 * A.W;
+  const size_t plane_off = ((size_t)s_idx * A.H + row0) * A.W;
   int16_t *const ref_t = A.ref + plane_off;
+  const unsigned char *const cur_t = static_cast<const unsigned char *>(A.curr) + plane_off * (SRC == SRC_U8 ? 1 : 2);
 
   // ---- 1. loads: all 2 * J 128-bit requests of the thread are in flight before first use --------
   uint32_t c_pk[J][4], r_pk[J][4];
@@ -56,11 +57,11 @@ __global__ void __launch_bounds__(256, 4) k_tile_fast(const __grid_constant__ Ti
     have[j] = q0 < npx;
     if (have[j]) {
       if (SRC == SRC_U8) {
-        const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(static_cast<const uint8_t *>(A.curr) + plane_off + q0));
+        const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(cur_t + q0));
         c_pk[j][0] = __byte_perm(v.x, 0, 0x4140); c_pk[j][1] = __byte_perm(v.x, 0, 0x4342);
         c_pk[j][2] = __byte_perm(v.y, 0, 0x4140); c_pk[j][3] = __byte_perm(v.y, 0, 0x4342);
       } else {
-        const uint4 v = ld16_stream(static_cast<const int16_t *>(A.curr) + plane_off + q0);
+        const uint4 v = ld16_stream(cur_t + 2 * q0);
         c_pk[j][0] = v.x; c_pk[j][1] = v.y; c_pk[j][2] = v.z; c_pk[j][3] = v.w;
       }
       const uint4 r = ld16(ref_t + q0);
@@ -86,11 +87,11 @@ __global__ void __launch_bounds__(256, 4) k_tile_fast(const __grid_constant__ Ti
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const uint32_t c = c_pk[j][w], r = r_pk[j][w];
-      rng |= r;
-      if (SRC != SRC_U8) rng |= c;
       a[w] = __vmaxu2(c, r) - __vminu2(c, r);  // no borrow: max >= min lane-wise
       fl[w] = (a[w] + kadd) & 0x80008000u;       // spike flags at bits 15 / 31
     }
+    rng |= (r_pk[j][0] | r_pk[j][1] | r_pk[j][2]) | r_pk[j][3];
+    if (SRC != SRC_U8) rng |= (c_pk[j][0] | c_pk[j][1] | c_pk[j][2]) | c_pk[j][3];
     if (fl[0] | fl[1] | fl[2] | fl[3]) {
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(256, 4) k_tile_fast(const __grid_constant__ Ti
     // kFastCap / NW rounded up to 32 -> at most 8 records per lane: the 8-bit histogram fields are safe
   }
   if (lane == 0) wtot[64 + warp] = w_pos | (w_neg << 16);
+  hist_flush(A, hist, nh, hp, hn, status);  // before the barrier: counters can then be written without another one
   __syncthreads();
   uint32_t base = 0, totals = 0;
   {
@@ -248,7 +250,240 @@ __global__ void __launch_bounds__(256, 4) k_tile_fast(const __grid_constant__ Ti
     for (int i = lane; i < (int)w_pos; i += 32) *reinterpret_cast<uint2 *>(pos_dst + i) = rec_sm[lo + i];
     for (int i = lane; i < (int)w_neg; i += 32) *reinterpret_cast<uint2 *>(neg_dst + i) = rec_sm[hi - 1 - i];
   }
-  tile_finish(A, s_idx, t_idx, hist, nh, n_pos_tile, n_neg_tile, hp, hn, status);
+  write_counters(A, s_idx, t_idx, hist, nh, n_pos_tile, n_neg_tile);
+}
+
+// ---- fast kernel, register-only variant ---------------------------------------------------------
+// Used when no shared-memory plane is needed: inhibition off (PAIR == false: thread owns JH groups in
+// linear order), or 2x2 inhibition with two-row tiles (PAIR == true: thread owns the SAME JH column
+// blocks in both rows of the tile, so each 2x2 area lives in one thread's registers and the arg-max
+// is taken before the work list is built -- only area winners become candidates).
+// shared memory: [wl: kFastCap u32][rec: kFastCap uint2][wtot: 128 u32][hist: 2 * (n_slots + 1) u32]
+template <int SRC, int JH, bool PAIR, bool SIMPLE>
+__global__ void __launch_bounds__(256, 4) k_tile_fast2(const __grid_constant__ TileArgs A) {
+  constexpr int J = PAIR ? 2 * JH : JH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
+  uint2 *rec_sm = reinterpret_cast<uint2 *>(smem_raw + kFastCap * 4);
+  uint32_t *wtot = reinterpret_cast<uint32_t *>(smem_raw + kFastCap * 12);
+  uint32_t *hist = wtot + 128;
+  const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+  const int t_idx = blockIdx.x, s_idx = blockIdx.y;
+  const int tile = s_idx * A.tiles_per_stream + t_idx;
+  const int row0 = t_idx * A.tile_rows;
+  const int npx = min(A.tile_rows, A.H - row0) * A.W;  // multiple of 8 (host-checked)
+  const size_t plane_off = ((size_t)s_idx * A.H + row0) * A.W;
+  int16_t *const ref_t = A.ref + plane_off;
+  const unsigned char *const cur_t = static_cast<const unsigned char *>(A.curr) + plane_off * (SRC == SRC_U8 ? 1 : 2);
+  const int gpr = A.W >> 3;  // groups of 8 pixels per row
+
+  // group j of this thread starts at tile-local pixel q0(j); PAIR: j = row * JH + column block
+  auto q0_of = [&](int j) -> int {
+    if (PAIR) { const int cg = (j % JH) * (int)blockDim.x + tid; return cg < gpr ? (j / JH) * A.W + cg * 8 : npx; }
+    return (j * (int)blockDim.x + tid) * 8;
+  };
+
+  // ---- 1. loads: all 2 * J 128-bit requests of the thread are in flight before first use --------
+  uint32_t c_pk[J][4], r_pk[J][4];
+  bool have[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int q0 = q0_of(j);
+    have[j] = q0 < npx;
+    if (have[j]) {
+      if (SRC == SRC_U8) {
+        const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(cur_t + q0));
+        c_pk[j][0] = __byte_perm(v.x, 0, 0x4140); c_pk[j][1] = __byte_perm(v.x, 0, 0x4342);
+        c_pk[j][2] = __byte_perm(v.y, 0, 0x4140); c_pk[j][3] = __byte_perm(v.y, 0, 0x4342);
+      } else {
+        const uint4 v = ld16_stream(cur_t + 2 * q0);
+        c_pk[j][0] = v.x; c_pk[j][1] = v.y; c_pk[j][2] = v.z; c_pk[j][3] = v.w;
+      }
+      const uint4 r = ld16(ref_t + q0);
+      r_pk[j][0] = r.x; r_pk[j][1] = r.y; r_pk[j][2] = r.z; r_pk[j][3] = r.w;
+    }
+  }
+  if (tid < 2 * nh) hist[tid] = 0;
+  for (int i = blockDim.x + tid; i < 2 * nh; i += blockDim.x) hist[i] = 0;
+
+  // ---- 2. packed threshold: a = max - min per u16 lane (masked to spiking lanes), spike iff a > T --
+  const int T = A.thr_scalar;                                  // 2 <= T <= 32767 (host-checked)
+  const uint32_t kadd = (uint32_t)(0x7fff - T) * 0x00010001u;  // bit 15 of (a + kadd) <=> a > T
+  uint32_t flags8[J];
+  uint32_t rng = 0, cnt_lo = 0, cnt_hi = 0;  // counts of groups (0,1) and (2,3), 16-bit fields
+  uint32_t a_pk[J][4];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    flags8[j] = 0;
+    if (!have[j]) continue;
+    uint32_t fl[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint32_t c = c_pk[j][w], r = r_pk[j][w];
+      const uint32_t a = __vmaxu2(c, r) - __vminu2(c, r);  // no borrow: max >= min lane-wise
+      fl[w] = (a + kadd) & 0x80008000u;                      // spike flags at bits 15 / 31
+      a_pk[j][w] = a;
+    }
+    rng |= (r_pk[j][0] | r_pk[j][1] | r_pk[j][2]) | r_pk[j][3];
+    if (SRC != SRC_U8) rng |= (c_pk[j][0] | c_pk[j][1] | c_pk[j][2]) | c_pk[j][3];
+    if (fl[0] | fl[1] | fl[2] | fl[3]) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        a_pk[j][w] &= (fl[w] >> 15) * 0xffffu;  // abs_diff * spikes
+        flags8[j] |= (((fl[w] >> 15) & 1u) | ((fl[w] >> 30) & 2u)) << (2 * w);
+      }
+    }
+  }
+  if (PAIR) {
+    // local_inhibition gs:177-221 on registers: of each 2x2 area (word w of the upper and of the lower
+    // row group) only the first arg-max of abs_diff * spikes keeps its spike (row-major, strict '>')
+#pragma unroll
+    for (int h = 0; h < JH; ++h) {
+      const int ju = h, jl = JH + h;
+      if ((flags8[ju] | flags8[jl]) == 0) continue;
+      uint32_t ku = 0, kl = 0;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t up = flags8[ju] ? a_pk[ju][w] : 0u, lo = flags8[jl] ? a_pk[jl][w] : 0u;
+        const int t00 = up & 0xffff, t01 = up >> 16, t10 = lo & 0xffff, t11 = lo >> 16;
+        int best = t00, bi = 0;
+        if (t01 > best) { best = t01; bi = 1; }
+        if (t10 > best) { best = t10; bi = 2; }
+        if (t11 > best) { best = t11; bi = 3; }
+        if (best > 0) {
+          if (bi < 2) ku |= 1u << (2 * w + bi); else kl |= 1u << (2 * w + bi - 2);
+        }
+      }
+      flags8[ju] = ku; flags8[jl] = kl;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const uint32_t n = __popc(flags8[j]);
+    if (j < 2) cnt_lo += n << (16 * (j & 1)); else cnt_hi += n << (16 * (j & 1));
+  }
+
+  // ---- 3. ordered work list: exclusive scan of the candidate counts in (group j, thread) order -----
+  const bool w_unsafe = __any_sync(kFull, (rng & 0xFF00FF00u) != 0);
+  const bool w_any = __any_sync(kFull, (cnt_lo | cnt_hi) != 0);
+  uint32_t in_lo = cnt_lo, in_hi = cnt_hi;
+  if (w_any) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y0 = __shfl_up_sync(kFull, in_lo, o), y1 = __shfl_up_sync(kFull, in_hi, o);
+      if (lane >= o) { in_lo += y0; in_hi += y1; }
+    }
+  }
+  if (lane == 31) {
+    wtot[0 * NW + warp] = in_lo & 0xffff;
+    if (J > 1) wtot[1 * NW + warp] = in_lo >> 16;
+    if (J > 2) { wtot[2 * NW + warp] = in_hi & 0xffff; wtot[3 * NW + warp] = in_hi >> 16; }
+    wtot[96 + warp] = w_unsafe ? 1u : 0u;
+  }
+  __syncthreads();
+  const uint32_t ent = lane < J * NW ? wtot[lane] : 0u;  // every warp scans the <= 32 totals redundantly
+  uint32_t ent_in = ent;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(kFull, ent_in, o);
+    if (lane >= o) ent_in += y;
+  }
+  const int n_cand = (int)__shfl_sync(kFull, ent_in, 31);
+  const bool unsafe = __any_sync(kFull, lane < NW && wtot[96 + lane] != 0);
+  if (n_cand == 0 && !unsafe) {  // quiet tile: no records, no events, reference untouched
+    for (int c = tid; c < A.C; c += blockDim.x)
+      A.tile_counts[((size_t)s_idx * A.C + c) * A.tiles_per_stream + t_idx] = 0;
+    return;
+  }
+  if (unsafe || n_cand > kFastCap) {  // generic body: exact int16 wrap semantics / dense tiles
+    if (tid == 0) A.redo[1 + atomicAdd(A.redo, 1)] = tile;
+    return;
+  }
+  {
+    // entry: tile-local pixel index (13 bits) | reference << 13 (8 bits) | abs_diff << 21 (8 bits) | negative << 29
+    const uint32_t ent_ex = ent_in - ent;
+    const uint32_t ex_lo = in_lo - cnt_lo, ex_hi = in_hi - cnt_hi;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const uint32_t base = __shfl_sync(kFull, ent_ex, j * NW + warp);
+      if (flags8[j] == 0) continue;
+      const int q0 = q0_of(j);
+      uint32_t pos = base + (((j < 2 ? ex_lo : ex_hi) >> (16 * (j & 1))) & 0xffffu);
+#pragma unroll
+      for (int p = 0; p < 8; ++p)
+        if ((flags8[j] >> p) & 1u) {
+          const int c = get16(c_pk[j], p), r = get16(r_pk[j], p);
+          wl[pos++] = (uint32_t)(q0 + p) | ((uint32_t)r << 13) | ((uint32_t)(c < r ? r - c : c - r) << 21) |
+                      (c < r ? 1u << 29 : 0u);
+        }
+    }
+  }
+  __syncthreads();
+
+  // ---- 4a. one candidate per lane: reference update, list membership, histogram, staged record ------
+  const int per_warp = (((n_cand + NW - 1) / NW) + 31) & ~31;
+  const int lo = min(n_cand, warp * per_warp), hi = min(n_cand, lo + per_warp);
+  const unsigned magic = A.upd.div_thr.magic;
+  const int max_n = A.upd.max_time_ms;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned long long hp = 0, hn = 0;
+  unsigned status = 0;
+  uint32_t w_pos = 0, w_neg = 0;
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    const int i = i0 + lane;
+    bool tp = false, tn = false;
+    uint2 rec = make_uint2(0u, 0u);
+    if (i < hi) {
+      const uint32_t e = wl[i];
+      const int q = e & 0x1fff, r = (e >> 13) & 0xff, a = (e >> 21) & 0xff;
+      const bool neg = (e >> 29) & 1u;
+      const int y = (int)__umulhi((unsigned)q, A.inv_w), x = q - y * A.W;
+      const int upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;  // update_reference_rate gs:244-249
+      ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
+      if (SIMPLE) {
+        tp = !neg; tn = neg;
+        const int k = max(0, (A.enc.n_slots - 1) - (int)__umulhi((unsigned)a, A.enc.dv.magic));  // gs:830-832
+        if (k < 8) { if (tp) hp += 1ull << (8 * k); else hn += 1ull << (8 * k); }
+      } else {
+        split_px(neg ? -1 : 1, A.polarity, A.uncoded, tp, tn);
+        if (tp || tn) hist_add(A, hist, nh, a, tp, hp, hn, status);
+      }
+      rec = make_uint2((uint32_t)(row0 + y) | ((uint32_t)x << 16), (uint32_t)a);
+    }
+    const unsigned bp = __ballot_sync(kFull, tp), bn = __ballot_sync(kFull, tn);
+    if (tp) rec_sm[lo + w_pos + __popc(bp & lt)] = rec;
+    if (tn) rec_sm[hi - 1 - (w_neg + __popc(bn & lt))] = rec;
+    w_pos += __popc(bp);
+    w_neg += __popc(bn);
+  }
+  if (lane == 0) wtot[64 + warp] = w_pos | (w_neg << 16);
+  hist_flush(A, hist, nh, hp, hn, status);
+  __syncthreads();
+  uint32_t base = 0, totals = 0;
+  {
+    const uint32_t t = lane < NW ? wtot[64 + lane] : 0u;
+    uint32_t t_in = t;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {  // NW <= 8
+      const uint32_t y = __shfl_up_sync(kFull, t_in, o);
+      if (lane >= o) t_in += y;
+    }
+    base = __shfl_sync(kFull, t_in - t, warp);
+    totals = __shfl_sync(kFull, t_in, 7);
+  }
+  const int n_pos_tile = totals & 0xffff, n_neg_tile = totals >> 16;
+
+  // ---- 4b. coalesced copy of the warp's staged records to their ranks in the tile's lists ----------
+  if (w_pos | w_neg) {
+    const size_t region = (size_t)tile * A.tile_px;
+    dvs_record *pos_dst = A.records + region + (base & 0xffff);
+    dvs_record *neg_dst = A.records + region + (A.tile_px - n_neg_tile) + (base >> 16);
+    for (int i = lane; i < (int)w_pos; i += 32) *reinterpret_cast<uint2 *>(pos_dst + i) = rec_sm[lo + i];
+    for (int i = lane; i < (int)w_neg; i += 32) *reinterpret_cast<uint2 *>(neg_dst + i) = rec_sm[hi - 1 - i];
+  }
+  write_counters(A, s_idx, t_idx, hist, nh, n_pos_tile, n_neg_tile);
 }
 
 template <int SRC, int J, int KI, bool SIMPLE>
@@ -277,6 +512,32 @@ static int launch_fast_shape(const TileArgs &A, int bd, size_t smem, cudaStream_
   return DVS_OK;
 }
 
+template <int SRC, int JH, bool PAIR, bool SIMPLE>
+static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
+  auto k = k_tile_fast2<SRC, JH, PAIR, SIMPLE>;
+  const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
+  const size_t smem = kFastCap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t);
+  cudaError_t e;
+  if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+    return set_error((int)e, cudaGetErrorString(e));
+  if ((e = cudaMemsetAsync(A.redo, 0, sizeof(int32_t), st)) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+  const long long tiles = (long long)A.S * A.tiles_per_stream;
+  k<<<dim3((unsigned)A.tiles_per_stream, (unsigned)A.S), bd, smem, st>>>(A);
+  if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+  // generic body over the (normally zero) declined tiles; its group-to-thread mapping is the linear one
+  constexpr int JR = (PAIR ? 2 * JH : JH) > 1 ? 4 : 1;
+  constexpr int KR = PAIR ? INH_K2 : INH_NONE;
+  auto kr = k_tile_redo<SRC, JR, KR>;
+  const size_t smem_r = ((KR != INH_NONE) ? ((A.tile_px * 2 + 15) & ~15) : 0) + (128 + 2 * nh + 8) * sizeof(uint32_t);
+  if (smem_r > 48 * 1024 && (e = cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)) != cudaSuccess)
+    return set_error((int)e, cudaGetErrorString(e));
+  const int items = A.tile_px / 8;
+  const int bd_r = JR == 1 ? (items + 31) / 32 * 32 : ((items + 3) / 4 + 31) / 32 * 32;
+  kr<<<(unsigned)(tiles < 592 ? tiles : 592), bd_r, smem_r, st>>>(A);
+  if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+  return DVS_OK;
+}
+
 // Caller guarantees: vec_ok, W % 8 == 0, <= 1024 groups per tile, inh_k in {1, 2}, 2 <= T, rate update,
 // history_weight == 1, max_time_ms >= 0, no debug planes.
 template <int SRC>
@@ -290,14 +551,30 @@ static int dispatch_fast(const TileArgs &A, cudaStream_t st) {
                       A.enc.uncoded == 0 && A.enc.n_slots <= 8 && A.enc.n_slots >= 1 && A.enc.threshold >= 2 &&
                       A.enc.u16_vals == 0 && A.fast_hist;
   auto round32 = [](int x) { return (x + 31) / 32 * 32; };
+  // register-only variant: no inhibition, or 2x2 inhibition on two-row tiles
+  if (!k2) {
+    if (items <= 256) {
+      const int bd = round32(items);
+      return simple ? launch_fast2<SRC, 1, false, true>(A, bd, st) : launch_fast2<SRC, 1, false, false>(A, bd, st);
+    }
+    const int bd = round32((items + 3) / 4);
+    return simple ? launch_fast2<SRC, 4, false, true>(A, bd, st) : launch_fast2<SRC, 4, false, false>(A, bd, st);
+  }
+  if (k2 && A.tile_rows == 2 && A.H % 2 == 0) {
+    const int gpr = A.W / 8;
+    if (gpr <= 256) {
+      const int bd = round32(gpr);
+      return simple ? launch_fast2<SRC, 1, true, true>(A, bd, st) : launch_fast2<SRC, 1, true, false>(A, bd, st);
+    }
+    const int bd = round32((gpr + 1) / 2);
+    return simple ? launch_fast2<SRC, 2, true, true>(A, bd, st) : launch_fast2<SRC, 2, true, false>(A, bd, st);
+  }
   if (items <= 256) {
     const int bd = round32(items);
-    if (simple) return k2 ? launch_fast_shape<SRC, 1, INH_K2, true>(A, bd, smem, st) : launch_fast_shape<SRC, 1, INH_NONE, true>(A, bd, smem, st);
-    return k2 ? launch_fast_shape<SRC, 1, INH_K2, false>(A, bd, smem, st) : launch_fast_shape<SRC, 1, INH_NONE, false>(A, bd, smem, st);
+    return simple ? launch_fast_shape<SRC, 1, INH_K2, true>(A, bd, smem, st) : launch_fast_shape<SRC, 1, INH_K2, false>(A, bd, smem, st);
   }
   const int bd = round32((items + 3) / 4);
-  if (simple) return k2 ? launch_fast_shape<SRC, 4, INH_K2, true>(A, bd, smem, st) : launch_fast_shape<SRC, 4, INH_NONE, true>(A, bd, smem, st);
-  return k2 ? launch_fast_shape<SRC, 4, INH_K2, false>(A, bd, smem, st) : launch_fast_shape<SRC, 4, INH_NONE, false>(A, bd, smem, st);
+  return simple ? launch_fast_shape<SRC, 4, INH_K2, true>(A, bd, smem, st) : launch_fast_shape<SRC, 4, INH_K2, false>(A, bd, smem, st);
 }
 
 }  // namespace dvs

@@ -101,12 +101,12 @@ DEV void hist_add(const TileArgs &A, uint32_t *hist, int nh, int a, bool tp, uns
   }
 }
 
-// Flush the register histograms (one redux.sync per pair of bins), publish the status bits and write
-// the tile's counters component-major: tile_counts[s][c][t].  Must be reached by every thread.
-DEV void tile_finish(const TileArgs &A, int s_idx, int t_idx, uint32_t *hist, int nh, int n_pos_tile,
-                     int n_neg_tile, unsigned long long hp, unsigned long long hn, unsigned status) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  if (A.enc.mode != DVS_ENC_NONE && A.fast_hist && (n_pos_tile | n_neg_tile) && __any_sync(kFull, (hp | hn) != 0)) {
+// Flush the register histograms into the shared-memory histogram (one redux.sync per pair of bins) and
+// publish the status bits.  Must be reached by every thread of the warp.
+DEV void hist_flush(const TileArgs &A, uint32_t *hist, int nh, unsigned long long hp, unsigned long long hn,
+                    unsigned status) {
+  const int lane = threadIdx.x & 31;
+  if (A.enc.mode != DVS_ENC_NONE && A.fast_hist && __any_sync(kFull, (hp | hn) != 0)) {
 #pragma unroll
     for (int w = 0; w < 8; ++w) {  // 16 bins (2 polarities x 8) as 8 words of two 16-bit fields
       const unsigned long long h = (w < 4) ? hp : hn;
@@ -122,8 +122,13 @@ DEV void tile_finish(const TileArgs &A, int s_idx, int t_idx, uint32_t *hist, in
   }
   status = __reduce_or_sync(kFull, status);
   if (status && lane == 0 && A.status) atomicOr(A.status, (int)status);
-  __syncthreads();
-  for (int c = tid; c < A.C; c += blockDim.x) {
+}
+
+// Write the tile's counters component-major: tile_counts[s][c][t].  Needs a barrier after the last
+// hist_flush / shared-memory atomic.
+DEV void write_counters(const TileArgs &A, int s_idx, int t_idx, const uint32_t *hist, int nh, int n_pos_tile,
+                        int n_neg_tile) {
+  for (int c = threadIdx.x; c < A.C; c += blockDim.x) {
     uint32_t v;
     if (c == 0) v = n_pos_tile;
     else if (c == 1) v = n_neg_tile;
@@ -137,6 +142,13 @@ DEV void tile_finish(const TileArgs &A, int s_idx, int t_idx, uint32_t *hist, in
     }
     A.tile_counts[((size_t)s_idx * A.C + c) * A.tiles_per_stream + t_idx] = v;
   }
+}
+
+DEV void tile_finish(const TileArgs &A, int s_idx, int t_idx, uint32_t *hist, int nh, int n_pos_tile,
+                     int n_neg_tile, unsigned long long hp, unsigned long long hn, unsigned status) {
+  hist_flush(A, hist, nh, hp, hn, status);
+  __syncthreads();
+  write_counters(A, s_idx, t_idx, hist, nh, n_pos_tile, n_neg_tile);
 }
 
 // ---- ordered compaction shared by the generic and the fast tile kernels ------------------------
