@@ -165,25 +165,100 @@ struct ExpandArgs {
   int32_t *status;
 };
 
+// grid = (ceil(2 * tiles_per_stream / 256), S).  Task index within a stream = pol * tps + t, so that the
+// 256 record counts a block looks at are two contiguous runs of tile_counts; every thread loads one
+// count (coalesced), and each warp then walks the non-empty tasks of its 32 lanes with the whole warp.
+// NS8 (n_slots <= 8, no time-binary multiplicities): every lane also pre-loads its own task's 8 segment
+// positions (coalesced over tiles) and the first records of the NEXT task are prefetched while the
+// current one is expanded, so the dependent-load chain per task is off the critical path.
+template <bool NS8>
 __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ ExpandArgs A) {
   const int lane = threadIdx.x & 31;
+  const int s = blockIdx.y;
+  const int my_task = blockIdx.x * blockDim.x + threadIdx.x;
+  const int my_pol = my_task >= A.tps, my_t = my_task - my_pol * A.tps;
+  int my_n = 0;
+  if (my_task < 2 * A.tps) {
+    my_n = (int)A.tile_counts[((size_t)s * A.C + my_pol) * A.tps + my_t];
+    // rate coding: slot 0 holds every record that emits at all -> tiles whose records all have k == 0
+    // (large changes emit nothing, Appendix A.8) are skipped without touching their records
+    if (my_n > 0 && A.enc.mode == DVS_ENC_RATE && A.tile_counts[((size_t)s * A.C + 2 + my_pol) * A.tps + my_t] == 0) my_n = 0;
+  }
+  unsigned todo = __ballot_sync(kFull, my_n > 0);
+  if (todo == 0) return;
   const long long n_seg = (long long)A.S * A.enc.n_slots * 2;
   if (A.seg_offsets[n_seg] > A.event_cap) {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && A.status) atomicOr(A.status, (int)DVS_STATUS_EVENT_OVERFLOW);
+    if (lane == 0 && A.status) atomicOr(A.status, (int)DVS_STATUS_EVENT_OVERFLOW);
     return;
   }
-  const long long n_tasks = 2ll * A.S * A.tps;
-  const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
   const bool bin_mode = A.enc.mode == DVS_ENC_TIME_BIN || A.enc.mode == DVS_ENC_TIME_BIN_THR;
+  const unsigned lt = (1u << lane) - 1u;
   unsigned status = 0;
-  for (long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < n_tasks;
-       task += warps_total) {
-    const long long tile = task >> 1;
-    const int pol = (int)(task & 1);
-    const int s = (int)(tile / A.tps), t = (int)(tile - (long long)s * A.tps);
-    const int n = (int)A.tile_counts[((size_t)s * A.C + pol) * A.tps + t];
-    if (n == 0) continue;
-    const dvs_record *rec = A.records + (size_t)tile * A.tile_px + (pol ? A.tile_px - n : 0);
+  const dvs_record *my_rec = A.records + ((size_t)s * A.tps + my_t) * A.tile_px + (my_pol ? A.tile_px - my_n : 0);
+
+  if (NS8) {
+    // this lane's task: position of its first event in each slot's segment, relative to the stream's events
+    const long long stream_base = A.seg_offsets[(long long)s * A.enc.n_slots * 2];
+    dvs_event *const ev_s = A.events + stream_base;
+    uint32_t my_base[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      my_base[j] = 0;
+      if (my_n > 0 && j < A.enc.n_slots)
+        my_base[j] = (uint32_t)(A.seg_offsets[((long long)s * A.enc.n_slots + j) * 2 + my_pol] - stream_base) +
+                     A.tile_excl[((size_t)s * A.C + 2 + 2 * j + my_pol) * A.tps + my_t];
+    }
+    int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const dvs_record *rec = reinterpret_cast<const dvs_record *>(__shfl_sync(kFull, (unsigned long long)my_rec, src));
+    int n = __shfl_sync(kFull, my_n, src);
+    uint2 r_first = lane < n ? *reinterpret_cast<const uint2 *>(rec + lane) : make_uint2(0, 0);
+    while (true) {
+      // prefetch the first chunk of the next task
+      const int nsrc = todo ? __ffs(todo) - 1 : -1;
+      const dvs_record *nrec = rec;
+      int nn = 0;
+      uint2 r_next = make_uint2(0, 0);
+      if (nsrc >= 0) {
+        todo &= todo - 1;
+        nrec = reinterpret_cast<const dvs_record *>(__shfl_sync(kFull, (unsigned long long)my_rec, nsrc));
+        nn = __shfl_sync(kFull, my_n, nsrc);
+        if (lane < nn) r_next = *reinterpret_cast<const uint2 *>(nrec + lane);
+      }
+      const int pol = __shfl_sync(kFull, my_pol, src);
+      uint32_t base[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) base[j] = __shfl_sync(kFull, my_base[j], src);
+      const uint32_t pbits = (pol ? 0xffffu : 1u) << 16;
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        uint2 r = r_first;
+        if (i0 > 0) r = i < n ? *reinterpret_cast<const uint2 *>(rec + i) : make_uint2(0, 0);
+        int desc = (A.enc.mode == DVS_ENC_TIME) ? -1 : 0;
+        if (i < n) desc = enc_desc(A.enc, (int)(short)(r.y & 0xffff), pol == 0, status);
+        const uint32_t xy = (r.x >> 16) | (r.x << 16);  // record is (row, col); event is (x = col, y = row)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool m = (A.enc.mode == DVS_ENC_RATE) ? desc > j : desc == j;
+          const unsigned bal = __ballot_sync(kFull, m);
+          if (m) *reinterpret_cast<uint2 *>(ev_s + base[j] + __popc(bal & lt)) = make_uint2(xy, (uint32_t)j | pbits);
+          base[j] += __popc(bal);
+        }
+      }
+      if (nsrc < 0) break;
+      src = nsrc; rec = nrec; n = nn; r_first = r_next;
+    }
+    status = __reduce_or_sync(kFull, status);
+    if (status && lane == 0 && A.status) atomicOr(A.status, (int)status);
+    return;
+  }
+
+  while (todo) {
+    const int src_lane = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int n = __shfl_sync(kFull, my_n, src_lane);
+    const int pol = __shfl_sync(kFull, my_pol, src_lane), t = __shfl_sync(kFull, my_t, src_lane);
+    const dvs_record *rec = reinterpret_cast<const dvs_record *>(__shfl_sync(kFull, (unsigned long long)my_rec, src_lane));
     for (int sb = 0; sb < A.enc.n_slots; sb += 32) {
       const int jmine = sb + lane;
       long long base = 0;
@@ -204,7 +279,7 @@ __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ ExpandAr
         }
         int jend = nj;
         if (A.enc.mode == DVS_ENC_RATE) jend = min(nj, max(0, __reduce_max_sync(kFull, desc) - sb));
-        const uint32_t xy = (r.x >> 16) | (r.x << 16);  // record is (row, col); event is (x=col, y=row)
+        const uint32_t xy = (r.x >> 16) | (r.x << 16);
         for (int jj = 0; jj < jend; ++jj) {
           const unsigned sm = __shfl_sync(kFull, slotmask, jj);
           const int m = enc_mult(A.enc, desc, sb + jj, sm);
@@ -213,7 +288,7 @@ __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ ExpandAr
           if (!bin_mode) {
             const unsigned bal = __ballot_sync(kFull, m != 0);
             tot = __popc(bal);
-            ex = __popc(bal & ((1u << lane) - 1u));
+            ex = __popc(bal & lt);
           } else {
             int x = m;
 #pragma unroll
@@ -680,12 +755,11 @@ int dvs_aer_expand(int32_t S, int32_t tiles_per_stream, int32_t tile_px, const d
   A.records = records; A.tile_counts = tile_counts; A.tile_excl = tile_excl;
   A.seg_offsets = reinterpret_cast<const long long *>(seg_offsets);
   A.events = events; A.event_cap = event_cap; A.status = status;
-  const long long n_tasks = 2ll * S * tiles_per_stream;
-  long long grid = (n_tasks + 7) / 8;
-  const long long cap = 148ll * 32;
-  if (grid > cap) grid = cap;
-  if (grid < 1) grid = 1;
-  k_expand<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(A);
+  if (S > 65535) return fail(DVS_ERR_UNSUPPORTED, "more than 65535 streams per launch");
+  const dim3 grid((unsigned)((2 * tiles_per_stream + 255) / 256), (unsigned)S);
+  const bool ns8 = (A.enc.mode == DVS_ENC_RATE || A.enc.mode == DVS_ENC_TIME) && A.enc.n_slots <= 8;
+  if (ns8) k_expand<true><<<grid, 256, 0, as_stream(stream)>>>(A);
+  else k_expand<false><<<grid, 256, 0, as_stream(stream)>>>(A);
   return check_launch("k_expand");
 }
 

@@ -22,6 +22,9 @@ DEV uint4 ld16_stream(const void *p) { return __ldcs(reinterpret_cast<const uint
 
 // shared memory of the fast kernel: [sd: tile_px int16][wl: tile_px uint16][code: tile_px uint8]
 //                                   [wtot: 128 u32][hist: 2 * (n_slots + 1) u32][misc: 8 u32]
+#ifndef FAST2_MINB
+#define FAST2_MINB 5
+#endif
 constexpr int kFastCap = 2048;  // work-list capacity; denser tiles go to the generic body (redo list)
 
 // shared memory: [sd: tile_px int16][wl: kFastCap u32][rec: kFastCap uint2][wtot: 128 u32]
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(256, 4) k_tile_fast(const __grid_constant__ Ti
 // is taken before the work list is built -- only area winners become candidates).
 // shared memory: [wl: kFastCap u32][rec: kFastCap uint2][wtot: 128 u32][hist: 2 * (n_slots + 1) u32]
 template <int SRC, int JH, bool PAIR, bool SIMPLE>
-__global__ void __launch_bounds__(256, 4) k_tile_fast2(const __grid_constant__ TileArgs A) {
+__global__ void __launch_bounds__(256, FAST2_MINB) k_tile_fast2(const __grid_constant__ TileArgs A) {
   constexpr int J = PAIR ? 2 * JH : JH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
