@@ -667,6 +667,13 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
                     !p->spikes_out && !p->force_generic && p->redo && A.S <= 65535;
   A.redo = p->redo;
   if (fast) return u8 ? launch_tile_fast_u8(A, st) : launch_tile_fast_i16(A, st);
+  // adaptive fast path: coded rate_adpt rule, no history decay, inhibition off or 2x2 on two-row tiles
+  const bool fast_adpt = p->adaptive && p->update_mode == DVS_UPD_RATE_ADPT && !p->uncoded && p->history_weight == 1.0 &&
+                         p->min_thr >= 0 && p->min_thr <= p->max_thr && p->max_thr <= 32767 && p->thr_up >= 0 &&
+                         p->thr_up <= 32767 && p->thr_down >= 0 && p->thr_down <= 32767 && A.vec_ok && A.W % 8 == 0 &&
+                         A.tile_px / 8 <= 1024 && (k == 1 || (k == 2 && A.tile_rows == 2 && A.H % 2 == 0)) &&
+                         !p->diff_out && !p->abs_diff_out && !p->spikes_out && !p->force_generic && p->redo && A.S <= 65535;
+  if (fast_adpt) return u8 ? launch_tile_fast_u8_adpt(A, st) : launch_tile_fast_i16_adpt(A, st);
   if (u8) return p->adaptive ? launch_tile_pass_u8_adpt(A, st) : launch_tile_pass_u8(A, st);
   return p->adaptive ? launch_tile_pass_i16_adpt(A, st) : launch_tile_pass_i16(A, st);
 }

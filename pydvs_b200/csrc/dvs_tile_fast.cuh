@@ -262,13 +262,18 @@ __global__ void __launch_bounds__(256, 4) k_tile_fast(const __grid_constant__ Ti
 // blocks in both rows of the tile, so each 2x2 area lives in one thread's registers and the arg-max
 // is taken before the work list is built -- only area winners become candidates).
 // shared memory: [wl: kFastCap u32][rec: kFastCap uint2][wtot: 128 u32][hist: 2 * (n_slots + 1) u32]
-template <int SRC, int JH, bool PAIR, bool SIMPLE>
-__global__ void __launch_bounds__(256, FAST2_MINB) k_tile_fast2(const __grid_constant__ TileArgs A) {
+// ADAPT: per-pixel threshold plane (thresholded_difference_adpt gs:83-113 + the coded
+// update_reference_rate_adpt gs:256-297): the plane is read with the frame, compared lane-wise, advanced
+// (+up where the pixel spikes after inhibition, -down elsewhere, clipped) on packed lanes and written back
+// for every pixel (10 B/px); the division abs_diff // threshold only happens for candidates.
+template <int SRC, int JH, bool PAIR, bool SIMPLE, bool ADAPT = false>
+__global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(const __grid_constant__ TileArgs A) {
   constexpr int J = PAIR ? 2 * JH : JH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
   uint2 *rec_sm = reinterpret_cast<uint2 *>(smem_raw + kFastCap * 4);
   uint32_t *wtot = reinterpret_cast<uint32_t *>(smem_raw + kFastCap * 12);
+  uint16_t *wl_thr = reinterpret_cast<uint16_t *>(wtot + 128 + 2 * (A.enc.mode == DVS_ENC_NONE ? 0 : A.enc.n_slots + 1) + 8);  // ADAPT
   uint32_t *hist = wtot + 128;
   const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
 
@@ -289,13 +294,18 @@ __global__ void __launch_bounds__(256, FAST2_MINB) k_tile_fast2(const __grid_con
   };
 
   // ---- 1. loads: all 2 * J 128-bit requests of the thread are in flight before first use --------
-  uint32_t c_pk[J][4], r_pk[J][4];
+  uint32_t c_pk[J][4], r_pk[J][4], t_pk[ADAPT ? J : 1][4];
   bool have[J];
+  int16_t *const thr_t = ADAPT ? A.thr + plane_off : nullptr;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int q0 = q0_of(j);
     have[j] = q0 < npx;
     if (have[j]) {
+      if (ADAPT) {
+        const uint4 t = ld16(thr_t + q0);
+        t_pk[j][0] = t.x; t_pk[j][1] = t.y; t_pk[j][2] = t.z; t_pk[j][3] = t.w;
+      }
       if (SRC == SRC_U8) {
         const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(cur_t + q0));
         c_pk[j][0] = __byte_perm(v.x, 0, 0x4140); c_pk[j][1] = __byte_perm(v.x, 0, 0x4342);
@@ -326,9 +336,11 @@ __global__ void __launch_bounds__(256, FAST2_MINB) k_tile_fast2(const __grid_con
     for (int w = 0; w < 4; ++w) {
       const uint32_t c = c_pk[j][w], r = r_pk[j][w];
       const uint32_t a = __vmaxu2(c, r) - __vminu2(c, r);  // no borrow: max >= min lane-wise
-      fl[w] = (a + kadd) & 0x80008000u;                      // spike flags at bits 15 / 31
+      if (ADAPT) fl[w] = ~((t_pk[j][w] | 0x80008000u) - a) & 0x80008000u;  // a > threshold lane-wise (both < 2^15)
+      else fl[w] = (a + kadd) & 0x80008000u;                 // spike flags at bits 15 / 31
       a_pk[j][w] = a;
     }
+    if (ADAPT) rng |= ((t_pk[j][0] | t_pk[j][1] | t_pk[j][2]) | t_pk[j][3]) & 0x80008000u ? 0xFF00u : 0u;  // negative threshold
     rng |= (r_pk[j][0] | r_pk[j][1] | r_pk[j][2]) | r_pk[j][3];
     if (SRC != SRC_U8) rng |= (c_pk[j][0] | c_pk[j][1] | c_pk[j][2]) | c_pk[j][3];
     if (fl[0] | fl[1] | fl[2] | fl[3]) {
@@ -362,6 +374,32 @@ __global__ void __launch_bounds__(256, FAST2_MINB) k_tile_fast2(const __grid_con
       flags8[ju] = ku; flags8[jl] = kl;
     }
   }
+  // update_reference_rate_adpt gs:291-297 on packed lanes: +up where the pixel still spikes, -down
+  // elsewhere, clipped to [min, max]; written back for every pixel.  Deferred until the tile is known to
+  // stay in this kernel (a declined tile must reach the generic body with its thresholds untouched).
+  auto store_thresholds = [&]() {
+    const uint32_t up2 = (uint32_t)A.upd.thr_up * 0x00010001u, dn2 = (uint32_t)A.upd.thr_down * 0x00010001u;
+    const uint32_t mn2 = (uint32_t)A.upd.min_thr * 0x00010001u, mx2 = (uint32_t)A.upd.max_thr * 0x00010001u;
+    const uint32_t mnd2 = mn2 + dn2;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      if (!have[j]) continue;
+      uint32_t tn[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t th = t_pk[j][w];
+        const uint32_t t_dn = __vminu2(__vmaxu2(th, mnd2) - dn2, mx2);   // clip(th - down, min, max)
+        uint32_t v = t_dn;
+        if (flags8[j]) {
+          const uint32_t t_up = __vminu2(__vmaxu2(th + up2, mn2), mx2);  // clip(th + up, min, max)
+          const uint32_t m = ((flags8[j] >> (2 * w)) & 1u) * 0xffffu | ((flags8[j] >> (2 * w + 1)) & 1u) * 0xffff0000u;
+          v = (t_up & m) | (t_dn & ~m);
+        }
+        tn[w] = v;
+      }
+      st16(thr_t + q0_of(j), tn);
+    }
+  };
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const uint32_t n = __popc(flags8[j]);
@@ -396,6 +434,7 @@ __global__ void __launch_bounds__(256, FAST2_MINB) k_tile_fast2(const __grid_con
   const int n_cand = (int)__shfl_sync(kFull, ent_in, 31);
   const bool unsafe = __any_sync(kFull, lane < NW && wtot[96 + lane] != 0);
   if (n_cand == 0 && !unsafe) {  // quiet tile: no records, no events, reference untouched
+    if (ADAPT) store_thresholds();
     for (int c = tid; c < A.C; c += blockDim.x)
       A.tile_counts[((size_t)s_idx * A.C + c) * A.tiles_per_stream + t_idx] = 0;
     return;
@@ -404,6 +443,7 @@ __global__ void __launch_bounds__(256, FAST2_MINB) k_tile_fast2(const __grid_con
     if (tid == 0) A.redo[1 + atomicAdd(A.redo, 1)] = tile;
     return;
   }
+  if (ADAPT) store_thresholds();
   {
     // entry: tile-local pixel index (13 bits) | reference << 13 (8 bits) | abs_diff << 21 (8 bits) | negative << 29
     const uint32_t ent_ex = ent_in - ent;
@@ -418,6 +458,7 @@ __global__ void __launch_bounds__(256, FAST2_MINB) k_tile_fast2(const __grid_con
       for (int p = 0; p < 8; ++p)
         if ((flags8[j] >> p) & 1u) {
           const int c = get16(c_pk[j], p), r = get16(r_pk[j], p);
+          if (ADAPT) wl_thr[pos] = (uint16_t)get16(t_pk[j], p);
           wl[pos++] = (uint32_t)(q0 + p) | ((uint32_t)r << 13) | ((uint32_t)(c < r ? r - c : c - r) << 21) |
                       (c < r ? 1u << 29 : 0u);
         }
@@ -443,7 +484,9 @@ __global__ void __launch_bounds__(256, FAST2_MINB) k_tile_fast2(const __grid_con
       const int q = e & 0x1fff, r = (e >> 13) & 0xff, a = (e >> 21) & 0xff;
       const bool neg = (e >> 29) & 1u;
       const int y = (int)__umulhi((unsigned)q, A.inv_w), x = q - y * A.W;
-      const int upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;  // update_reference_rate gs:244-249
+      int upd;
+      if (ADAPT) upd = np_floordiv(a, (int)wl_thr[i]) * A.upd.min_thr;       // gs:287-289: (a // thr) * min_threshold
+      else upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;          // update_reference_rate gs:244-249
       ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
       if (SIMPLE) {
         tp = !neg; tn = neg;
@@ -515,11 +558,11 @@ static int launch_fast_shape(const TileArgs &A, int bd, size_t smem, cudaStream_
   return DVS_OK;
 }
 
-template <int SRC, int JH, bool PAIR, bool SIMPLE>
+template <int SRC, int JH, bool PAIR, bool SIMPLE, bool ADAPT = false>
 static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
-  auto k = k_tile_fast2<SRC, JH, PAIR, SIMPLE>;
+  auto k = k_tile_fast2<SRC, JH, PAIR, SIMPLE, ADAPT>;
   const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
-  const size_t smem = kFastCap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t);
+  const size_t smem = kFastCap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t) + (ADAPT ? kFastCap * 2 : 0);
   cudaError_t e;
   if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
     return set_error((int)e, cudaGetErrorString(e));
@@ -530,7 +573,7 @@ static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
   // generic body over the (normally zero) declined tiles; its group-to-thread mapping is the linear one
   constexpr int JR = (PAIR ? 2 * JH : JH) > 1 ? 4 : 1;
   constexpr int KR = PAIR ? INH_K2 : INH_NONE;
-  auto kr = k_tile_redo<SRC, JR, KR>;
+  auto kr = k_tile_redo<SRC, JR, KR, ADAPT>;
   const size_t smem_r = ((KR != INH_NONE) ? ((A.tile_px * 2 + 15) & ~15) : 0) + (128 + 2 * nh + 8) * sizeof(uint32_t);
   if (smem_r > 48 * 1024 && (e = cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)) != cudaSuccess)
     return set_error((int)e, cudaGetErrorString(e));
@@ -578,6 +621,22 @@ static int dispatch_fast(const TileArgs &A, cudaStream_t st) {
   }
   const int bd = round32((items + 3) / 4);
   return simple ? launch_fast_shape<SRC, 4, INH_K2, true>(A, bd, smem, st) : launch_fast_shape<SRC, 4, INH_K2, false>(A, bd, smem, st);
+}
+
+// Adaptive-threshold fast path.  Caller guarantees: vec_ok (incl. the threshold plane), W % 8 == 0,
+// <= 1024 groups per tile, inhibition off or 2x2 on two-row tiles, coded rate_adpt update with
+// history_weight == 1, 0 <= min <= max <= 32767, 0 <= up, down <= 32767.
+template <int SRC>
+static int dispatch_fast_adpt(const TileArgs &A, cudaStream_t st) {
+  const int items = A.tile_px / 8;
+  auto round32 = [](int x) { return (x + 31) / 32 * 32; };
+  if (A.inh_k != 2) {
+    if (items <= 256) return launch_fast2<SRC, 1, false, false, true>(A, round32(items), st);
+    return launch_fast2<SRC, 4, false, false, true>(A, round32((items + 3) / 4), st);
+  }
+  const int gpr = A.W / 8;
+  if (gpr <= 256) return launch_fast2<SRC, 1, true, false, true>(A, round32(gpr), st);
+  return launch_fast2<SRC, 2, true, false, true>(A, round32((gpr + 1) / 2), st);
 }
 
 }  // namespace dvs

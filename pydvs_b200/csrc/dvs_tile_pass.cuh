@@ -411,11 +411,11 @@ __global__ void __launch_bounds__(BDMAX) k_tile_pass(const __grid_constant__ Til
 
 // Generic body over the tiles the fast kernel declined (pixels outside [0, 255]): A.redo[0] = count,
 // A.redo[1..] = tile indices.  Launched after every fast pass; normally finds count == 0.
-template <int SRC, int J, int KI>
+template <int SRC, int J, int KI, bool ADAPT = false>
 __global__ void __launch_bounds__(256) k_tile_redo(const __grid_constant__ TileArgs A) {
   const int n = A.redo[0];
   for (int i = blockIdx.x; i < n; i += gridDim.x) {
-    tile_body<SRC, J, false, KI>(A, A.redo[1 + i]);
+    tile_body<SRC, J, ADAPT, KI>(A, A.redo[1 + i]);
     __syncthreads();  // shared memory is reused by the next tile
   }
 }
@@ -475,5 +475,8 @@ int launch_tile_pass_planes(const TileArgs &A, cudaStream_t st);
 // fast path (dvs_tile_fast.cuh): static threshold, rate update, history_weight == 1
 int launch_tile_fast_i16(const TileArgs &A, cudaStream_t st);
 int launch_tile_fast_u8(const TileArgs &A, cudaStream_t st);
+// fast path with a per-pixel adaptive threshold plane (coded update_reference_rate_adpt, history_weight == 1)
+int launch_tile_fast_i16_adpt(const TileArgs &A, cudaStream_t st);
+int launch_tile_fast_u8_adpt(const TileArgs &A, cudaStream_t st);
 
 }  // namespace dvs

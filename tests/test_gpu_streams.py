@@ -207,6 +207,29 @@ def test_fast_kernel_falls_back_outside_8bit_range():
     _run_case(2, 16, 256, source="wide", frames=3, debug=True)           # and the generic kernel itself
 
 
+def test_fast_adaptive_kernel():
+    # coded rate_adpt rule with history_weight == 1 -> k_tile_fast2<ADAPT>
+    _run_case(5, 54, 96, output_type="TIME", adaptive=True, max_time_ms=4, num_bins=4, source="bar", frames=8, thr0=12,
+              debug=False)
+    _run_case(2, 8, 1920, output_type="TIME", adaptive=True, max_time_ms=4, num_bins=4, source="bar", frames=6, thr0=12,
+              debug=False)                                                            # J = 1, wide rows
+    _run_case(2, 4, 3840, output_type="RATE", adaptive=True, source="random", frames=5, thr0=12, debug=False)  # J = 4
+    _run_case(2, 8, 1920, output_type="RATE", adaptive=True, inh=2, source="random", frames=6, thr0=12, debug=False)  # PAIR
+    _run_case(2, 8, 3840, output_type="TIME", adaptive=True, inh=2, num_bins=8, source="bar", frames=6, thr0=12,
+              debug=False)                                                            # PAIR, two column blocks
+    _run_case(2, 16, 64, output_type="RATE", adaptive=True, frame_dtype="uint8", frames=5, thr0=12, debug=False)
+    _run_case(2, 16, 64, output_type="RATE", adaptive=True, frames=5, thr0=0, debug=False)      # zero thresholds (B.2)
+    _run_case(2, 16, 64, output_type="RATE", adaptive=True, frames=5, thr0=500, debug=False)    # above max: clipped down
+    _run_case(2, 16, 64, output_type="TIME_BIN_THR", adaptive=True, num_bins=6, frames=5, thr0=12, debug=False,
+              source="narrow", ref0=100)
+
+
+def test_fast_adaptive_kernel_declines_out_of_range_tiles():
+    _run_case(2, 16, 256, output_type="RATE", adaptive=True, source="wide", frames=4, thr0=12, debug=False)
+    _run_case(2, 16, 256, output_type="RATE", adaptive=True, frames=4, thr0=-7, debug=False)    # negative thresholds
+    _run_case(1, 8, 1920, output_type="RATE", adaptive=True, inh=2, source="wide", frames=3, thr0=12, debug=False)
+
+
 def test_event_overflow_is_recoverable():
     from pydvs_b200 import DVSConfig, DVSStreams, synth
     cfg = DVSConfig(width=64, height=32, streams=2, output_type="RATE")
