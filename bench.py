@@ -326,7 +326,8 @@ def run_ours(args, wl, rank, local_rank, world):
                     adaptive_threshold=wl["adaptive"], history_weight=wl["hw"], max_time_ms=wl["max_time_ms"],
                     num_bins=wl["num_bins"], inh_area_width=wl["inh"], frame_dtype=args.frame_dtype,
                     threshold0=12 if wl["adaptive"] else None)
-    per_px_events = 1.0 if args.pattern == "bar" else 2.0  # frame 0 is dense (ref0 = 128 vs background 64)
+    # frame 0 is dense (ref0 = 128 vs background 64): ~2 events per pixel, a quarter of that with 2x2 inhibition
+    per_px_events = (1.0 if wl["inh"] > 1 else 3.0) if args.pattern == "bar" else 3.0
     dvs = DVSStreams(cfg, device=device, event_capacity=int(max(1 << 20, S * P * per_px_events)))
     ring = make_ring(wl, S, args.ring, args.pattern, args.frame_dtype, device, stream_base)
     torch.cuda.synchronize()

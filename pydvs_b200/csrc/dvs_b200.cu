@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(1024) k_scan_segments(int S, int n_slots, cons
 // K3: expand records into events, one warp per (tile, polarity)
 // ================================================================================================
 struct ExpandArgs {
-  int S, tps, tile_px, C;
+  int S, tps, tile_px, C, tpw;
   EncArgs enc;
   const dvs_record *records;
   const uint32_t *tile_counts, *tile_excl;
@@ -175,7 +175,9 @@ template <bool NS8>
 __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ ExpandArgs A) {
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.y;
-  const int my_task = blockIdx.x * blockDim.x + threadIdx.x;
+  // A.tpw tasks per warp (32 when there are plenty of tiles, fewer to keep >= ~16k warps in flight)
+  const int warp_g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int my_task = lane < A.tpw ? warp_g * A.tpw + lane : 2 * A.tps;
   const int my_pol = my_task >= A.tps, my_t = my_task - my_pol * A.tps;
   int my_n = 0;
   if (my_task < 2 * A.tps) {
@@ -230,19 +232,31 @@ __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ ExpandAr
 #pragma unroll
       for (int j = 0; j < 8; ++j) base[j] = __shfl_sync(kFull, my_base[j], src);
       const uint32_t pbits = (pol ? 0xffffu : 1u) << 16;
-      for (int i0 = 0; i0 < n; i0 += 32) {
-        const int i = i0 + lane;
-        uint2 r = r_first;
-        if (i0 > 0) r = i < n ? *reinterpret_cast<const uint2 *>(rec + i) : make_uint2(0, 0);
-        int desc = (A.enc.mode == DVS_ENC_TIME) ? -1 : 0;
-        if (i < n) desc = enc_desc(A.enc, (int)(short)(r.y & 0xffff), pol == 0, status);
-        const uint32_t xy = (r.x >> 16) | (r.x << 16);  // record is (row, col); event is (x = col, y = row)
+      // four 32-record chunks per iteration: their loads are issued back to back (4x the bytes in flight)
+      for (int i0 = 0; i0 < n; i0 += 128) {
+        uint2 rr[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const bool m = (A.enc.mode == DVS_ENC_RATE) ? desc > j : desc == j;
-          const unsigned bal = __ballot_sync(kFull, m);
-          if (m) *reinterpret_cast<uint2 *>(ev_s + base[j] + __popc(bal & lt)) = make_uint2(xy, (uint32_t)j | pbits);
-          base[j] += __popc(bal);
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + 32 * u + lane;
+          rr[u] = (u == 0 && i0 == 0) ? r_first : (i < n ? *reinterpret_cast<const uint2 *>(rec + i) : make_uint2(0, 0));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (i0 + 32 * u >= n) break;
+          const int i = i0 + 32 * u + lane;
+          const uint2 r = rr[u];
+          int desc = (A.enc.mode == DVS_ENC_TIME) ? -1 : 0;
+          if (i < n) desc = enc_desc(A.enc, (int)(short)(r.y & 0xffff), pol == 0, status);
+          const uint32_t xy = (r.x >> 16) | (r.x << 16);  // record is (row, col); event is (x = col, y = row)
+          const int dmax = __reduce_max_sync(kFull, desc);
+          if (A.enc.mode == DVS_ENC_RATE && dmax <= 0) continue;  // nothing in this chunk emits
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const bool m = (A.enc.mode == DVS_ENC_RATE) ? desc > j : desc == j;
+            const unsigned bal = __ballot_sync(kFull, m);
+            if (m) *reinterpret_cast<uint2 *>(ev_s + base[j] + __popc(bal & lt)) = make_uint2(xy, (uint32_t)j | pbits);
+            base[j] += __popc(bal);
+          }
         }
       }
       if (nsrc < 0) break;
@@ -763,7 +777,11 @@ int dvs_aer_expand(int32_t S, int32_t tiles_per_stream, int32_t tile_px, const d
   A.seg_offsets = reinterpret_cast<const long long *>(seg_offsets);
   A.events = events; A.event_cap = event_cap; A.status = status;
   if (S > 65535) return fail(DVS_ERR_UNSUPPORTED, "more than 65535 streams per launch");
-  const dim3 grid((unsigned)((2 * tiles_per_stream + 255) / 256), (unsigned)S);
+  int tpw = 32;
+  while (tpw > 1 && (long long)S * ((2 * tiles_per_stream + tpw - 1) / tpw) < 16384) tpw >>= 1;
+  A.tpw = tpw;
+  const int tasks_per_block = 8 * tpw;
+  const dim3 grid((unsigned)((2 * tiles_per_stream + tasks_per_block - 1) / tasks_per_block), (unsigned)S);
   const bool ns8 = (A.enc.mode == DVS_ENC_RATE || A.enc.mode == DVS_ENC_TIME) && A.enc.n_slots <= 8;
   if (ns8) k_expand<true><<<grid, 256, 0, as_stream(stream)>>>(A);
   else k_expand<false><<<grid, 256, 0, as_stream(stream)>>>(A);
