@@ -273,6 +273,27 @@ class DVSStreams:
         check(lib.dvs_scan_tiles(self.S, self.tps, self.n_slots, _ptr(self.tile_counts), _ptr(self.tile_excl),
                                  _ptr(self.stream_totals), _ptr(self.seg_offsets), current_stream_ptr()))
 
+    # -- CUDA-graph replay for launch-bound (small) configurations ---------------------------------
+    def capture(self, frames: torch.Tensor):
+        """Capture one step (all launches) reading from the static buffer ``frames`` into a CUDA graph.
+        Copy each new frame into ``frames`` and call ``replay()``: one graph launch instead of six
+        launches from Python (128x128 / 640x480 single streams are launch-bound)."""
+        self.step(frames)          # warm-up outside the capture: function attributes, lazy module load
+        torch.cuda.synchronize()
+        self.ref_snapshot = None
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.tile_pass(frames)
+            self.scan()
+            self.expand()
+        self._graph, self._graph_frames = graph, frames
+        return graph
+
+    def replay(self) -> StepResult:
+        self._graph.replay()
+        self.frames_done += 1
+        return StepResult(self, self.events, self.seg_offsets, self.status)
+
     def expand(self):
         check(lib.dvs_aer_expand(self.S, self.tps, self.tile_px, C.byref(self._enc), _ptr(self.records),
                                  _ptr(self.tile_counts), _ptr(self.tile_excl), _ptr(self.seg_offsets),

@@ -230,6 +230,23 @@ def test_fast_adaptive_kernel_declines_out_of_range_tiles():
     _run_case(1, 8, 1920, output_type="RATE", adaptive=True, inh=2, source="wide", frames=3, thr0=12, debug=False)
 
 
+def test_cuda_graph_replay_matches_eager_steps():
+    from pydvs_b200 import DVSConfig, DVSStreams, synth
+    cfg = DVSConfig(width=128, height=128, streams=1, output_type="RATE", inh_area_width=2)
+    eager, graphed = DVSStreams(cfg), DVSStreams(cfg)
+    static = synth.moving_bar(1, 128, 128, 0, noise=6, seed=1)
+    eager.step(static)
+    graphed.capture(static)            # performs step 0 as its warm-up ...
+    graphed.ref.copy_(eager.ref)       # ... and the capture pass itself launches nothing
+    for t in range(1, 8):
+        f = synth.moving_bar(1, 128, 128, t, noise=6, seed=1)
+        re = eager.step(f)
+        static.copy_(f)
+        rg = graphed.replay()
+        assert torch.equal(eager.ref, graphed.ref)
+        assert torch.equal(re.seg_offsets, rg.seg_offsets) and torch.equal(re.events(), rg.events())
+
+
 def test_event_overflow_is_recoverable():
     from pydvs_b200 import DVSConfig, DVSStreams, synth
     cfg = DVSConfig(width=64, height=32, streams=2, output_type="RATE")
