@@ -675,14 +675,21 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
              (!p->spikes_out || aligned16(p->spikes_out));
   cudaStream_t st = as_stream(stream);
   // fast path: static threshold, rate update, no history decay, vector-friendly geometry
-  const bool fast = !p->adaptive && p->update_mode == DVS_UPD_RATE && p->history_weight == 1.0 &&
+  // (the register-only kernels also take 0 <= history_weight < 1 and the time-binary updates)
+  const bool plain = p->update_mode == DVS_UPD_RATE && p->history_weight == 1.0;
+  const bool regs_only = k == 1 || (k == 2 && A.tile_rows == 2 && A.H % 2 == 0);
+  const bool upd_ok = plain || (regs_only && p->history_weight >= 0.0 && p->history_weight <= 1.0 &&
+                                (p->update_mode == DVS_UPD_RATE || p->update_mode == DVS_UPD_TIME_BIN_RAW ||
+                                 (p->update_mode == DVS_UPD_TIME_BIN_THR && p->threshold <= 128)));
+  const bool fast = !p->adaptive && upd_ok &&
                     p->threshold >= 2 && p->threshold <= 32767 && p->max_time_ms >= 0 && A.vec_ok &&
                     A.W % 8 == 0 && A.tile_px / 8 <= 1024 && k <= 2 && !p->diff_out && !p->abs_diff_out &&
                     !p->spikes_out && !p->force_generic && p->redo && A.S <= 65535;
   A.redo = p->redo;
   if (fast) return u8 ? launch_tile_fast_u8(A, st) : launch_tile_fast_i16(A, st);
   // adaptive fast path: coded rate_adpt rule, no history decay, inhibition off or 2x2 on two-row tiles
-  const bool fast_adpt = p->adaptive && p->update_mode == DVS_UPD_RATE_ADPT && !p->uncoded && p->history_weight == 1.0 &&
+  const bool fast_adpt = p->adaptive && p->update_mode == DVS_UPD_RATE_ADPT && !p->uncoded &&
+                         p->history_weight >= 0.0 && p->history_weight <= 1.0 &&
                          p->min_thr >= 0 && p->min_thr <= p->max_thr && p->max_thr <= 32767 && p->thr_up >= 0 &&
                          p->thr_up <= 32767 && p->thr_down >= 0 && p->thr_down <= 32767 && A.vec_ok && A.W % 8 == 0 &&
                          A.tile_px / 8 <= 1024 && (k == 1 || (k == 2 && A.tile_rows == 2 && A.H % 2 == 0)) &&

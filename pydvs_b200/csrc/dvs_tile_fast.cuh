@@ -274,6 +274,8 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
   uint2 *rec_sm = reinterpret_cast<uint2 *>(smem_raw + kFastCap * 4);
   uint32_t *wtot = reinterpret_cast<uint32_t *>(smem_raw + kFastCap * 12);
   uint16_t *wl_thr = reinterpret_cast<uint16_t *>(wtot + 128 + 2 * (A.enc.mode == DVS_ENC_NONE ? 0 : A.enc.n_slots + 1) + 8);  // ADAPT
+  uint8_t *tr_lut = reinterpret_cast<uint8_t *>(wl_thr + (ADAPT ? kFastCap : 0));  // history_weight != 1: trunc(hw * r), r in [0, 255]
+  const bool decay = !SIMPLE && A.upd.hw_is_one == 0;  // (SIMPLE implies plain rate update, no decay) 0 <= history_weight < 1 (host-checked): every pixel's reference moves
   uint32_t *hist = wtot + 128;
   const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
 
@@ -320,6 +322,8 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
   }
   if (tid < 2 * nh) hist[tid] = 0;
   for (int i = blockDim.x + tid; i < 2 * nh; i += blockDim.x) hist[i] = 0;
+  if (decay)  // DTYPE(history_weight * ref_frame) gs:249 for every possible in-range reference value, exact in fp64
+    for (int i = tid; i < 256; i += blockDim.x) tr_lut[i] = (uint8_t)hist_weight(A.upd.hw, false, i);
 
   // ---- 2. packed threshold: a = max - min per u16 lane (masked to spiking lanes), spike iff a > T --
   const int T = A.thr_scalar;                                  // 2 <= T <= 32767 (host-checked)
@@ -400,6 +404,19 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
       st16(thr_t + q0_of(j), tn);
     }
   };
+  // history_weight != 1: the reference of every pixel decays (clip(trunc(hw * r) + 0, 0, 255)); candidates are
+  // overwritten with their full update in step 4a.  Deferred like the thresholds (needs the LUT barrier too).
+  auto store_decayed_reference = [&]() {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      if (!have[j]) continue;
+      uint32_t rn[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        rn[w] = (uint32_t)tr_lut[r_pk[j][w] & 0xff] | ((uint32_t)tr_lut[(r_pk[j][w] >> 16) & 0xff] << 16);
+      st16(ref_t + q0_of(j), rn);
+    }
+  };
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const uint32_t n = __popc(flags8[j]);
@@ -433,8 +450,9 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
   }
   const int n_cand = (int)__shfl_sync(kFull, ent_in, 31);
   const bool unsafe = __any_sync(kFull, lane < NW && wtot[96 + lane] != 0);
-  if (n_cand == 0 && !unsafe) {  // quiet tile: no records, no events, reference untouched
+  if (n_cand == 0 && !unsafe) {  // quiet tile: no records, no events, reference untouched (unless it decays)
     if (ADAPT) store_thresholds();
+    if (decay) store_decayed_reference();
     for (int c = tid; c < A.C; c += blockDim.x)
       A.tile_counts[((size_t)s_idx * A.C + c) * A.tiles_per_stream + t_idx] = 0;
     return;
@@ -444,6 +462,7 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
     return;
   }
   if (ADAPT) store_thresholds();
+  if (decay) store_decayed_reference();
   {
     // entry: tile-local pixel index (13 bits) | reference << 13 (8 bits) | abs_diff << 21 (8 bits) | negative << 29
     const uint32_t ent_ex = ent_in - ent;
@@ -459,8 +478,9 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
         if ((flags8[j] >> p) & 1u) {
           const int c = get16(c_pk[j], p), r = get16(r_pk[j], p);
           if (ADAPT) wl_thr[pos] = (uint16_t)get16(t_pk[j], p);
-          wl[pos++] = (uint32_t)(q0 + p) | ((uint32_t)r << 13) | ((uint32_t)(c < r ? r - c : c - r) << 21) |
-                      (c < r ? 1u << 29 : 0u);
+          // the entry carries the reference the update starts from: trunc(history_weight * r)
+          wl[pos++] = (uint32_t)(q0 + p) | ((uint32_t)(decay ? (int)tr_lut[r] : r) << 13) |
+                      ((uint32_t)(c < r ? r - c : c - r) << 21) | (c < r ? 1u << 29 : 0u);
         }
     }
   }
@@ -486,7 +506,13 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
       const int y = (int)__umulhi((unsigned)q, A.inv_w), x = q - y * A.W;
       int upd;
       if (ADAPT) upd = np_floordiv(a, (int)wl_thr[i]) * A.upd.min_thr;       // gs:287-289: (a // thr) * min_threshold
-      else upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;          // update_reference_rate gs:244-249
+      else if (SIMPLE || A.upd.mode == DVS_UPD_RATE) upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;  // gs:244-249
+      else {  // time-binary updates gs:374-376 / gs:421-423: log2 table of abs_diff (raw) or of abs_diff // T
+        const int idx = A.upd.mode == DVS_UPD_TIME_BIN_THR ? (int)__umulhi((unsigned)a, magic) : a;
+        upd = 0;
+        if (idx >= A.upd.lut_len) status |= DVS_STATUS_LUT_INDEX;
+        else upd = (int)__ldg(A.upd.lut + idx) * (A.upd.mode == DVS_UPD_TIME_BIN_THR ? T : 1);
+      }
       ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
       if (SIMPLE) {
         tp = !neg; tn = neg;
@@ -562,7 +588,7 @@ template <int SRC, int JH, bool PAIR, bool SIMPLE, bool ADAPT = false>
 static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
   auto k = k_tile_fast2<SRC, JH, PAIR, SIMPLE, ADAPT>;
   const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
-  const size_t smem = kFastCap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t) + (ADAPT ? kFastCap * 2 : 0);
+  const size_t smem = kFastCap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t) + (ADAPT ? kFastCap * 2 : 0) + 256;
   cudaError_t e;
   if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
     return set_error((int)e, cudaGetErrorString(e));
@@ -595,7 +621,7 @@ static int dispatch_fast(const TileArgs &A, cudaStream_t st) {
   // inlined membership / histogram: MERGED or uncoded lists, coded RATE encoder, <= 8 slots, threshold >= 2
   const bool simple = (A.uncoded == 0 && A.polarity == DVS_POL_MERGED) && A.enc.mode == DVS_ENC_RATE &&
                       A.enc.uncoded == 0 && A.enc.n_slots <= 8 && A.enc.n_slots >= 1 && A.enc.threshold >= 2 &&
-                      A.enc.u16_vals == 0 && A.fast_hist;
+                      A.enc.u16_vals == 0 && A.fast_hist && A.upd.mode == DVS_UPD_RATE && A.upd.hw_is_one;
   auto round32 = [](int x) { return (x + 31) / 32 * 32; };
   // register-only variant: no inhibition, or 2x2 inhibition on two-row tiles
   if (!k2) {

@@ -224,6 +224,22 @@ def test_fast_adaptive_kernel():
               source="narrow", ref0=100)
 
 
+def test_fast_kernel_history_decay_and_time_binary_updates():
+    for hw in (0.99, 0.5, 0.29, 0.0):
+        _run_case(2, 16, 64, hw=hw, frames=5, source="narrow", debug=False)
+    _run_case(2, 8, 1920, hw=0.99, inh=2, frames=5, source="bar", debug=False)                      # PAIR + decay
+    _run_case(2, 16, 64, hw=0.9, adaptive=True, frames=5, thr0=12, debug=False)                     # ADAPT + decay
+    _run_case(48, 32, 32, output_type="TIME_BIN_THR", adaptive=True, hw=0.99, frames=8, source="narrow", ref0=0,
+              num_bins=6, threshold=12, thr0=12, debug=False)                                       # BASELINE cfg 2 shape
+    _run_case(2, 24, 40, output_type="TIME_BIN", num_bins=8, frames=4, source="narrow", lut_bits=(3, 8), threshold=5,
+              debug=False)                                                                          # time_binary_raw update
+    _run_case(2, 24, 40, output_type="TIME_BIN_THR", num_bins=6, frames=4, source="narrow", threshold=5, debug=False)
+    _run_case(1, 128, 128, output_type="TIME_BIN_THR", num_bins=6, inh=2, frames=6, source="bar", threshold=12,
+              debug=False)                                                                          # stand_alone.py's loop
+    _run_case(2, 8, 1920, output_type="TIME_BIN_THR", num_bins=6, inh=2, hw=0.99, frames=4, source="narrow", threshold=6,
+              debug=False)
+
+
 def test_fast_adaptive_kernel_declines_out_of_range_tiles():
     _run_case(2, 16, 256, output_type="RATE", adaptive=True, source="wide", frames=4, thr0=12, debug=False)
     _run_case(2, 16, 256, output_type="RATE", adaptive=True, frames=4, thr0=-7, debug=False)    # negative thresholds
