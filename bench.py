@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--frame-dtype", default="int16", choices=["int16", "uint8"])
     ap.add_argument("--ring", type=int, default=4, help="distinct frames resident per stream")
     ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-frame-dtype", default="both", choices=["int16", "uint8", "both"],
+                    help="dtype of the HOST frames of the e2e leg: uint8 = camera-native bytes (the reference's callers "
+                         "widen to int16 on the host, stand_alone.py:50), int16 = the reference API's own dtype")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=3)
@@ -407,7 +410,23 @@ def run_ours(args, wl, rank, local_rank, world):
     # ---- e2e: host frames in pinned memory, H2D + step + D2H of the AER result per step --------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, dvs, ring, S, P, device, world, barrier)
+        kinds = ["uint8", "int16"] if args.e2e_frame_dtype == "both" else [args.e2e_frame_dtype]
+        legs = {}
+        for kind in kinds:
+            if kind == args.frame_dtype:
+                legs[kind] = run_e2e(args, dvs, ring, S, P, device, world, barrier, kind)
+            else:  # same streams, other input dtype: its own state object, frames converted once (untimed)
+                cfg2 = DVSConfig(**{**cfg.__dict__, "frame_dtype": kind})
+                dvs2 = DVSStreams(cfg2, device=device, event_capacity=dvs.event_capacity)
+                ring2 = [f.to(torch.uint8 if kind == "uint8" else torch.int16) for f in ring]
+                for i in range(max(args.settle, 0) + 3):
+                    dvs2.step(ring2[i % len(ring2)])
+                legs[kind] = run_e2e(args, dvs2, ring2, S, P, device, world, barrier, kind)
+                del dvs2, ring2
+                torch.cuda.empty_cache()
+        e2e = legs[kinds[0]]
+        if len(kinds) > 1:
+            e2e["other_host_dtype"] = legs[kinds[1]]
 
     if rank != 0:
         return
@@ -460,14 +479,14 @@ def run_ours(args, wl, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_e2e(args, dvs, ring, S, P, device, world, barrier):
+def run_e2e(args, dvs, ring, S, P, device, world, barrier, frame_dtype):
     """Same metric through the public API with HOST buffers: every step copies that step's frames
     from pinned host memory to the device, runs the step, and reads the AER result (CSR row pointers
     + events) back to pinned host memory.  H2D of step i+1 overlaps compute / D2H of step i."""
     import psutil
     import torch
     import torch.distributed as dist
-    elem = 1 if args.frame_dtype == "uint8" else 2
+    elem = 1 if frame_dtype == "uint8" else 2
     frame_bytes = S * P * elem
     n_host = 2
     avail = psutil.virtual_memory().available
@@ -524,7 +543,7 @@ def run_e2e(args, dvs, ring, S, P, device, world, barrier):
     dvs.check_status()
     value = S * world * K / secs
     return {"value": value, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": d2h_total // K,
-            "steps": K, "gpixel_per_s": value * P / 1e9, "host_frame_dtype": args.frame_dtype,
+            "steps": K, "gpixel_per_s": value * P / 1e9, "host_frame_dtype": frame_dtype,
             "note": "pinned host frames -> H2D -> fused step -> D2H of CSR offsets + events, per step; PCIe-bound"}
 
 
