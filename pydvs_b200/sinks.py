@@ -1,0 +1,68 @@
+"""AER sinks -- the step AFTER the hot path: the text spike-file format of
+``mnist_to_spikes.py:290-310`` / ``sequence_to_spikes.py:292-311`` (one ``"<key> <time_ms>"`` line per event,
+slot j of a frame stamped ``t_frame + j * t_bin_ms``) and the per-slot pacing rule of
+``ExternalDvsEmulatorDevice.calculate_time_per_pack`` (``external_dvs_emulator_device.py:700-715``).
+
+Host-side formatting over the CSR result of a step (one D2H copy of keys + offsets per stream); works on a
+``SpikeLists`` / ``StepResult`` from the CUDA path as well as on plain lists of lists.
+"""
+import io
+
+import numpy as np
+
+from .spike_lists import SpikeLists
+from .streams import OUTPUT_RATE, OUTPUT_TIME, OUTPUT_TIME_BIN
+
+
+def _keys_and_offsets(lists):
+    if isinstance(lists, SpikeLists):
+        keys = lists.payload
+        keys = keys.cpu().numpy() if hasattr(keys, "cpu") else np.asarray(keys)
+        off = lists.slot_offsets
+        off = off.cpu().numpy() if hasattr(off, "cpu") else np.asarray(off)
+        return keys, np.asarray(off, dtype=np.int64) - int(off[0])
+    off = np.cumsum([0] + [len(x) for x in lists]).astype(np.int64)
+    keys = np.array([k for sl in lists for k in sl], dtype=np.int64)
+    return keys, off
+
+
+def spike_file_lines(lists, t_frame_ms, t_bin_ms):
+    """The lines ``mnist_to_spikes.py:290-298`` appends for one frame: ``"%s %f" % (key, t + t_idx)``."""
+    keys, off = _keys_and_offsets(lists)
+    if keys.ndim != 1:
+        raise ValueError("spike files hold 16-bit keys; the uncoded rate/time encoders emit (row, col, p) triples")
+    slots = np.repeat(np.arange(len(off) - 1), np.diff(off))
+    times = float(t_frame_ms) + slots.astype(np.float64) * float(t_bin_ms)
+    return ["%s %f" % (int(k), t) for k, t in zip(keys.tolist(), times.tolist())]
+
+
+class SpikeFileWriter:
+    """Accumulates frames of one stream like the reference's ``write_buff`` and writes them joined by newlines
+    (no trailing newline), ``mnist_to_spikes.py:308-310``."""
+
+    def __init__(self, frame_time_ms, t_bin_ms):
+        self.frame_time_ms, self.t_bin_ms = frame_time_ms, t_bin_ms
+        self.t = 0
+        self.lines = []
+
+    def add_frame(self, lists):
+        self.lines += spike_file_lines(lists, self.t, self.t_bin_ms)
+        self.t += self.frame_time_ms
+
+    def getvalue(self):
+        return "\n".join(self.lines)
+
+    def write(self, path):
+        with io.open(path, "w") as f:
+            f.write(self.getvalue())
+
+
+def calculate_time_per_pack(output_type, max_time_ms, min_threshold, max_threshold, num_bits_per_spike):
+    """Milliseconds between two slot packets, ``external_dvs_emulator_device.py:700-715``."""
+    if output_type == OUTPUT_RATE:
+        return 1
+    if output_type == OUTPUT_TIME:
+        return max_time_ms // min(max_time_ms, max_threshold // min_threshold + 1)
+    if output_type == OUTPUT_TIME_BIN:
+        return max_time_ms // 8
+    return max_time_ms // (num_bits_per_spike + 1)
