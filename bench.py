@@ -558,6 +558,17 @@ def main():
         return
     import torch
     import torch.distributed as dist
+    lib_path = os.path.join(ROOT, "pydvs_b200", "libpydvs_b200.so")
+    if not os.path.exists(lib_path):  # fresh checkout: build the real thing (there is no fallback to fall back to)
+        if local_rank == 0:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_pydvs_build", os.path.join(ROOT, "pydvs_b200", "build.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        else:
+            while not os.path.exists(lib_path + ".sha256"):
+                time.sleep(1.0)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))

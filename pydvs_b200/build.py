@@ -81,5 +81,15 @@ def build(force=False, verbose=True, ptxas_verbose=False):
     return LIB
 
 
+def ensure_built(verbose=True):
+    """Build the library if it is missing or older than its sources (used by the tests, smoke() and
+    bench.py so that a fresh checkout works on a box that has nvcc)."""
+    if not up_to_date():
+        if verbose:
+            print("[pydvs_b200] libpydvs_b200.so missing or stale: building with nvcc ...", flush=True)
+        build(verbose=verbose)
+    return LIB
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, ptxas_verbose="-v" in sys.argv)

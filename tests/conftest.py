@@ -10,6 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the product has no CPU fallback: make sure the CUDA library exists before anything imports it
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_pydvs_build", os.path.join(ROOT, "pydvs_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if not os.path.exists(mod.LIB):
+        mod.build()
 
 
 def _has_gpu():
