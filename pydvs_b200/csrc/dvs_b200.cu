@@ -688,7 +688,11 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
   A.redo = p->redo;
   if (fast) return u8 ? launch_tile_fast_u8(A, st) : launch_tile_fast_i16(A, st);
   // adaptive fast path: coded rate_adpt rule, no history decay, inhibition off or 2x2 on two-row tiles
-  const bool fast_adpt = p->adaptive && p->update_mode == DVS_UPD_RATE_ADPT && !p->uncoded &&
+  // (uncoded rule: th - down must not borrow below zero lane-wise, so thresholds start and stay >= down is not
+  //  guaranteed -> require min_thr >= 0 and let the range vote catch negative planes; th > min >= 0 => th - down
+  //  can go negative only if down > th - 0, which the generic body handles: restrict to down <= min_thr + 1)
+  const bool unc_ok = !p->uncoded || (p->thr_down <= p->min_thr + 1);
+  const bool fast_adpt = p->adaptive && p->update_mode == DVS_UPD_RATE_ADPT && unc_ok &&
                          p->history_weight >= 0.0 && p->history_weight <= 1.0 &&
                          p->min_thr >= 0 && p->min_thr <= p->max_thr && p->max_thr <= 32767 && p->thr_up >= 0 &&
                          p->thr_up <= 32767 && p->thr_down >= 0 && p->thr_down <= 32767 && A.vec_ok && A.W % 8 == 0 &&

@@ -392,10 +392,20 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         const uint32_t th = t_pk[j][w];
-        const uint32_t t_dn = __vminu2(__vmaxu2(th, mnd2) - dn2, mx2);   // clip(th - down, min, max)
+        uint32_t t_dn, t_up = 0;
+        if (!A.upd.uncoded) {
+          t_dn = __vminu2(__vmaxu2(th, mnd2) - dn2, mx2);                // clip(th - down, min, max)
+          if (flags8[j]) t_up = __vminu2(__vmaxu2(th + up2, mn2), mx2);  // clip(th + up, min, max)
+        } else {
+          // uncoded twin gsu:286-295: += up only while th < max, -= down only while th > min, no clip.
+          // lane-wise compare of values < 2^15: bit 15 of ((x | 0x8000) - y) is set iff x >= y
+          const uint32_t ge_max = ((th | 0x80008000u) - mx2) & 0x80008000u;       // th >= max
+          const uint32_t le_min = ((mn2 | 0x80008000u) - th) & 0x80008000u;       // min >= th
+          t_dn = th - (dn2 & ~((le_min >> 15) * 0xffffu));                        // th - down where th > min
+          if (flags8[j]) t_up = th + (up2 & ~((ge_max >> 15) * 0xffffu));         // th + up where th < max
+        }
         uint32_t v = t_dn;
         if (flags8[j]) {
-          const uint32_t t_up = __vminu2(__vmaxu2(th + up2, mn2), mx2);  // clip(th + up, min, max)
           const uint32_t m = ((flags8[j] >> (2 * w)) & 1u) * 0xffffu | ((flags8[j] >> (2 * w + 1)) & 1u) * 0xffff0000u;
           v = (t_up & m) | (t_dn & ~m);
         }

@@ -240,6 +240,14 @@ def test_fast_kernel_history_decay_and_time_binary_updates():
               debug=False)
 
 
+def test_fast_adaptive_kernel_uncoded_rule():
+    # generate_spikes_uncoded.pyx:281-295: guarded +/- without a final clip (can undershoot min by down - 1)
+    _run_case(2, 16, 64, output_type="RATE", adaptive=True, uncoded=True, frames=8, thr0=7, debug=False)
+    _run_case(2, 8, 1920, output_type="TIME", adaptive=True, uncoded=True, inh=2, num_bins=8, frames=6, thr0=12,
+              source="bar", debug=False)
+    _run_case(2, 16, 64, output_type="RATE", adaptive=True, uncoded=True, frames=6, thr0=200, debug=False)  # above max
+
+
 def test_fast_adaptive_kernel_declines_out_of_range_tiles():
     _run_case(2, 16, 256, output_type="RATE", adaptive=True, source="wide", frames=4, thr0=12, debug=False)
     _run_case(2, 16, 256, output_type="RATE", adaptive=True, frames=4, thr0=-7, debug=False)    # negative thresholds
