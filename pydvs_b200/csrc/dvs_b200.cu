@@ -1,15 +1,14 @@
-// dvs_b200.cu -- sm_100a kernels + C-ABI of libpydvs_b200 (see include/pydvs_b200.h).
+// dvs_b200.cu -- C-ABI of libpydvs_b200 (include/pydvs_b200.h) and every kernel except the fused tile pass.
 //
 // Data path of one frame over S streams (DESIGN.md has the full account):
-//   K1 k_tile_pass   one CTA per tile (tile_rows full-width rows of one stream): 128-bit loads of
-//                    frame/reference(/threshold), threshold + sign split, k x k inhibition staged in
-//                    shared memory, reference (+ adaptive threshold) update written back in place,
-//                    ordered compaction of the spiking pixels into the tile's record list
-//                    (shuffle scans, 16-bit packed pos|neg counters) and the tile's per-slot event
-//                    counts (register histograms + redux.sync, or shared-memory atomics).
-//   K2 k_scan_*      exclusive scans of the per-tile counters -> CSR row pointers.
-//   K3 k_expand      one warp per (tile, polarity): ballot/popc expansion of records into
-//                    (x, y, t, p) events at their final, reference-ordered positions.
+//   K1 tile pass   csrc/dvs_tile_fast.cuh (specialised) / csrc/dvs_tile_pass.cuh (generic), instantiated in
+//                  tile_*.cu: threshold + sign split, k x k inhibition, reference (+ adaptive threshold)
+//                  update in place, ordered compaction of the spiking pixels into the tile's record lists,
+//                  per-tile per-slot event counts.
+//   K2 k_scan_*    exclusive scans of the per-tile counters -> CSR row pointers (this file).
+//   K3 k_expand    ballot/popc expansion of records into (x, y, t, p) events at their final,
+//                  reference-ordered positions (this file).
+//   plus the unfused 1:1 kernels behind the drop-in module functions and the float32 DVSOperator mode.
 // Everything is HBM-bound integer work: no tensor cores, no TMEM.
 #include <cuda_runtime.h>
 #include <limits.h>

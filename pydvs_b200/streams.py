@@ -13,8 +13,7 @@ and of the C++ ``PyDVS`` object that owns ``_ref/_thr`` (``pydvs/cpp/dvs_emu.hpp
 PyTorch is used for device memory and streams only.
 """
 import ctypes as C
-import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional
 
 import numpy as np

@@ -1,5 +1,10 @@
-import torch, sys
-sys.path.insert(0,'/root/repo')
+"""Per-kernel CUDA-event timing of the step over the frame ring (K1 / scans / expand), 64 streams of 4K."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pydvs_b200 import DVSConfig, DVSStreams, synth
 import bench
 wl = bench.WORKLOADS["4k_full_pipeline_rate"]
