@@ -234,6 +234,16 @@ int dvs_gather_split(int32_t s, int32_t tiles_per_stream, int32_t tile_px, int32
 int dvs_keys_from_events(const dvs_event *events, int64_t n, int32_t uncoded, int32_t flag_shift,
                          int32_t data_shift, int32_t data_mask, int16_t *keys, void *stream);
 
+/* ---- frame sources (the step before the hot path) ----------------- */
+
+/* Batched move_image gs:1184-1215 (what usaccade_image gs:1218-1242 / attention_image apply) followed by the
+ * optional mask_image gs:1124-1127: stream s shows images[img_index[s]] shifted right by dx[s] and up by
+ * dy[s]; vacated pixels = bg; with a mask (float64 [H][W]) out = int16(trunc(moved * mask)).
+ * images: [n_images][H][W] int16, out: [S][H][W] int16. */
+int dvs_move_mask_i16(const int16_t *images, int32_t n_images, const int32_t *img_index, const int32_t *dx,
+                      const int32_t *dy, int32_t bg, const double *mask, int16_t *out, int32_t S, int32_t H,
+                      int32_t W, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

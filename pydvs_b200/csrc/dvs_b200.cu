@@ -536,6 +536,25 @@ __global__ void __launch_bounds__(256) k_keys_from_events(const dvs_event *__res
   keys[i] = (int16_t)spike_key(y, x, p > 0, uncoded, flag_shift, data_shift, data_mask);
 }
 
+// batched move_image (+ mask_image): one thread per output pixel, gs:1184-1215 / gs:1124-1127
+__global__ void __launch_bounds__(256) k_move_mask(const int16_t *__restrict__ images, int n_images,
+                                                   const int32_t *__restrict__ img_index, const int32_t *__restrict__ dx,
+                                                   const int32_t *__restrict__ dy, int bg, const double *__restrict__ mask,
+                                                   int16_t *__restrict__ out, int S, int H, int W) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long P = (long long)H * W;
+  if (g >= (long long)S * P) return;
+  const int s = (int)(g / P);
+  const int q = (int)(g - (long long)s * P);
+  const int y = q / W, x = q - y * W;
+  const int sx = x - dx[s], sy = y + dy[s];  // content moves right for dx > 0 and up for dy > 0
+  int v = bg;
+  const int img = img_index[s];
+  if (sx >= 0 && sx < W && sy >= 0 && sy < H && img >= 0 && img < n_images) v = images[(long long)img * P + (long long)sy * W + sx];
+  if (mask) v = w16(__double2int_rz((double)v * mask[q]));  // DTYPE(original * mask)
+  out[g] = (int16_t)v;
+}
+
 }  // namespace dvs
 
 // ================================================================================================
@@ -887,6 +906,17 @@ int dvs_step_f32(const float *src, float *diff, float *ref, float *thr, float re
   const long long groups = (n_px + 3) / 4;
   k_step_f32<<<(unsigned)((groups + 255) / 256), 256, 0, as_stream(stream)>>>(src, diff, ref, thr, relax, up, down, n_px, vec);
   return check_launch("k_step_f32");
+}
+
+int dvs_move_mask_i16(const int16_t *images, int32_t n_images, const int32_t *img_index, const int32_t *dx,
+                      const int32_t *dy, int32_t bg, const double *mask, int16_t *out, int32_t S, int32_t H, int32_t W,
+                      void *stream) {
+  if (!images || !img_index || !dx || !dy || !out || n_images <= 0 || S <= 0 || H <= 0 || W <= 0)
+    return fail(DVS_ERR_INVALID_ARGUMENT, "move_mask arguments");
+  const long long n = (long long)S * H * W;
+  k_move_mask<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(images, n_images, img_index, dx, dy, bg, mask, out,
+                                                                       S, H, W);
+  return check_launch("k_move_mask");
 }
 
 int dvs_keys_from_events(const dvs_event *events, int64_t n, int32_t uncoded, int32_t flag_shift, int32_t data_shift,

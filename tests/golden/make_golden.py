@@ -185,6 +185,16 @@ def main():
         neg, pos, g = gs.split_spikes(s, a, pol)
         out["split_p%d_neg" % pol], out["split_p%d_pos" % pol], out["split_p%d_g" % pol] = neg, pos, np.int64(g)
 
+    # frame animators: usaccade_image on a frame where it only moves (frame % frames_per_usaccade != 0), then mask
+    digit = cv2.imread(pngs[0], cv2.IMREAD_GRAYSCALE)
+    padded = np.zeros((32, 32), dtype=np.int16)
+    padded[2:30, 2:30] = digit
+    moves = [(0, 0), (1, 0), (0, 1), (-1, -1), (2, -3), (-5, 4), (31, 0), (0, -32), (40, 40)]
+    out["move_src"], out["move_mask"] = padded, mask
+    out["move_offsets"] = np.array(moves, dtype=np.int32)
+    out["move_plain"] = np.stack([gs.usaccade_image(padded, 3, 2, 1, cx, cy, 9)[0] for cx, cy in moves])
+    out["move_masked"] = np.stack([gs.mask_image(gs.usaccade_image(padded, 3, 2, 1, cx, cy, 0)[0], mask) for cx, cy in moves])
+
     path = os.path.join(HERE, "golden_v1.npz")
     np.savez_compressed(path, **out)
     print("wrote %s (%.1f KiB, %d arrays)" % (path, os.path.getsize(path) / 1024, len(out)))
