@@ -483,15 +483,22 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
       if (flags8[j] == 0) continue;
       const int q0 = q0_of(j);
       uint32_t pos = base + (((j < 2 ? ex_lo : ex_hi) >> (16 * (j & 1))) & 0xffffu);
-#pragma unroll
-      for (int p = 0; p < 8; ++p)
-        if ((flags8[j] >> p) & 1u) {
-          const int c = get16(c_pk[j], p), r = get16(r_pk[j], p);
-          if (ADAPT) wl_thr[pos] = (uint16_t)get16(t_pk[j], p);
+      const unsigned long long c_lo = ((unsigned long long)c_pk[j][1] << 32) | c_pk[j][0], c_hi = ((unsigned long long)c_pk[j][3] << 32) | c_pk[j][2];
+      const unsigned long long r_lo = ((unsigned long long)r_pk[j][1] << 32) | r_pk[j][0], r_hi = ((unsigned long long)r_pk[j][3] << 32) | r_pk[j][2];
+      for (uint32_t m = flags8[j]; m; m &= m - 1) {  // candidates only (at most 4 per group after 2x2 inhibition)
+        const int p = __ffs(m) - 1;
+        {
+          const int sh = 16 * (p & 3);
+          const int c = (int)(((p < 4 ? c_lo : c_hi) >> sh) & 0xffff), r = (int)(((p < 4 ? r_lo : r_hi) >> sh) & 0xffff);
+          if (ADAPT) {
+            const unsigned long long t_lo = ((unsigned long long)t_pk[j][1] << 32) | t_pk[j][0], t_hi = ((unsigned long long)t_pk[j][3] << 32) | t_pk[j][2];
+            wl_thr[pos] = (uint16_t)((p < 4 ? t_lo : t_hi) >> sh);
+          }
           // the entry carries the reference the update starts from: trunc(history_weight * r)
           wl[pos++] = (uint32_t)(q0 + p) | ((uint32_t)(decay ? (int)tr_lut[r] : r) << 13) |
                       ((uint32_t)(c < r ? r - c : c - r) << 21) | (c < r ? 1u << 29 : 0u);
         }
+      }
     }
   }
   __syncthreads();
@@ -527,7 +534,7 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
       if (SIMPLE) {
         tp = !neg; tn = neg;
         const int k = max(0, (A.enc.n_slots - 1) - (int)__umulhi((unsigned)a, A.enc.dv.magic));  // gs:830-832
-        if (k < 8) { if (tp) hp += 1ull << (8 * k); else hn += 1ull << (8 * k); }
+        atomicAdd(&hist[(neg ? nh : 0) + k], 1u);  // fire-and-forget shared-memory reduction (k <= n_slots - 1)
       } else {
         split_px(neg ? -1 : 1, A.polarity, A.uncoded, tp, tn);
         if (tp || tn) hist_add(A, hist, nh, a, tp, hp, hn, status);
@@ -541,7 +548,7 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
     w_neg += __popc(bn);
   }
   if (lane == 0) wtot[64 + warp] = w_pos | (w_neg << 16);
-  hist_flush(A, hist, nh, hp, hn, status);
+  if (!SIMPLE) hist_flush(A, hist, nh, hp, hn, status);
   __syncthreads();
   uint32_t base = 0, totals = 0;
   {
