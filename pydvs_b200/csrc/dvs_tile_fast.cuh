@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
         atomicAdd(&hist[(neg ? nh : 0) + k], 1u);  // fire-and-forget shared-memory reduction (k <= n_slots - 1)
       } else {
         split_px(neg ? -1 : 1, A.polarity, A.uncoded, tp, tn);
-        if (tp || tn) hist_add(A, hist, nh, a, tp, hp, hn, status);
+        if (tp || tn) hist_add(A, hist, nh, a, tp, hp, hn, status, /*allow_regs=*/false);
       }
       rec = make_uint2((uint32_t)(row0 + y) | ((uint32_t)x << 16), (uint32_t)a);
     }
@@ -548,7 +548,10 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
     w_neg += __popc(bn);
   }
   if (lane == 0) wtot[64 + warp] = w_pos | (w_neg << 16);
-  if (!SIMPLE) hist_flush(A, hist, nh, hp, hn, status);
+  if (!SIMPLE) {  // only the status bits are left to publish: the histogram went straight to shared memory
+    status = __reduce_or_sync(kFull, status);
+    if (status && lane == 0 && A.status) atomicOr(A.status, (int)status);
+  }
   __syncthreads();
   uint32_t base = 0, totals = 0;
   {

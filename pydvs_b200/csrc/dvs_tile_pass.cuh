@@ -81,15 +81,15 @@ DEV uint32_t sgn_code(int s) { return s > 0 ? 1u : (s < 0 ? 2u : 0u); }
 // n_slots <= 8): 8-bit fields of two 64-bit registers per thread (callers add < 256 records per
 // thread between flushes); otherwise shared-memory atomics.
 DEV void hist_add(const TileArgs &A, uint32_t *hist, int nh, int a, bool tp, unsigned long long &hp,
-                  unsigned long long &hn, unsigned &status) {
+                  unsigned long long &hn, unsigned &status, bool allow_regs = true) {
   if (A.enc.mode == DVS_ENC_NONE) return;
   const int desc = enc_desc(A.enc, a, tp, status);
-  if (A.fast_hist) {  // desc in [-1, 8]
+  if (A.fast_hist && allow_regs) {  // desc in [-1, 8]
     if (desc >= 0 && desc < 8) {
       if (tp) hp += 1ull << (8 * desc); else hn += 1ull << (8 * desc);
     }
   } else if (A.enc.mode == DVS_ENC_RATE || A.enc.mode == DVS_ENC_TIME) {
-    if (desc >= 0) atomicAdd(&hist[(tp ? 0 : nh) + desc], 1u);
+    if (desc >= 0 && desc < nh) atomicAdd(&hist[(tp ? 0 : nh) + desc], 1u);
   } else {
     for (int jj = 0; jj < A.enc.n_slots; ++jj) {
       unsigned inv;
