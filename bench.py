@@ -64,6 +64,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=3)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--pipeline-depth", type=int, default=1, choices=[1, 2],
+                    help="2: double-buffer records/counters/events and run the AER expand of step n on a side "
+                         "stream while the tile pass of step n+1 runs (steady-state streaming); 1: in line")
     ap.add_argument("--graph", action="store_true", help="replay the step as one CUDA graph (launch-bound configs)")
     ap.add_argument("--settle", type=int, default=24,
                     help="untimed steps before the warm-up: with inhibition only one pixel of each 2x2 area moves "
@@ -332,7 +335,8 @@ def run_ours(args, wl, rank, local_rank, world):
                     threshold0=12 if wl["adaptive"] else None)
     # frame 0 is dense (ref0 = 128 vs background 64): ~2 events per pixel, a quarter of that with 2x2 inhibition
     per_px_events = (1.0 if wl["inh"] > 1 else 3.0) if args.pattern == "bar" else 3.0
-    dvs = DVSStreams(cfg, device=device, event_capacity=int(max(1 << 20, S * P * per_px_events)))
+    depth = 1 if args.graph else args.pipeline_depth
+    dvs = DVSStreams(cfg, device=device, event_capacity=int(max(1 << 20, S * P * per_px_events)), pipeline_depth=depth)
     ring = make_ring(wl, S, args.ring, args.pattern, args.frame_dtype, device, stream_base)
     torch.cuda.synchronize()
 
@@ -373,12 +377,14 @@ def run_ours(args, wl, rank, local_rank, world):
         for i in range(K):
             f = ring[step_i % args.ring]
             step_i += 1
+            dvs.begin_step()
             ev[i][0].record()
             dvs.tile_pass(f)
             ev[i][1].record()
             dvs.scan()
-            dvs.expand()
+            dvs.expand_async()
             ev[i][2].record()
+        dvs.drain()   # every side-stream expand finishes inside the timed region
     stop.record()
     torch.cuda.synchronize()
     barrier()
@@ -417,7 +423,7 @@ def run_ours(args, wl, rank, local_rank, world):
                 legs[kind] = run_e2e(args, dvs, ring, S, P, device, world, barrier, kind)
             else:  # same streams, other input dtype: its own state object, frames converted once (untimed)
                 cfg2 = DVSConfig(**{**cfg.__dict__, "frame_dtype": kind})
-                dvs2 = DVSStreams(cfg2, device=device, event_capacity=dvs.event_capacity)
+                dvs2 = DVSStreams(cfg2, device=device, event_capacity=dvs.event_capacity)  # e2e legs run in line
                 ring2 = [f.to(torch.uint8 if kind == "uint8" else torch.int16) for f in ring]
                 for i in range(max(args.settle, 0) + 3):
                     dvs2.step(ring2[i % len(ring2)])
@@ -459,7 +465,7 @@ def run_ours(args, wl, rank, local_rank, world):
         "config": {"workload": args.workload, "width": W, "height": H, "streams_per_gpu": S,
                    "streams_total": total_streams, "coding": wl["output_type"], "inhibition": wl["inh"],
                    "adaptive_threshold": wl["adaptive"], "pattern": args.pattern, "frame_dtype": args.frame_dtype,
-                   "ring_frames": args.ring, "settle_steps": args.settle, "l2": "inputs larger than L2 (%.1f GB touched per step)" % (step_bytes / 1e9),
+                   "ring_frames": args.ring, "settle_steps": args.settle, "pipeline_depth": depth, "l2": "inputs larger than L2 (%.1f GB touched per step)" % (step_bytes / 1e9),
                    "events_last_step": events_last_step, "tile_rows": dvs.tile_rows},
         "roofline": {"bound": "hbm", "kernel": "k_tile_pass (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

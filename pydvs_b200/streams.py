@@ -98,13 +98,21 @@ class StepResult:
     (SURVEY.md Appendix A.7).  Each event is 8 bytes: uint16 x, y, t and int16 p.
     """
 
-    def __init__(self, owner, events, seg_offsets, status):
+    def __init__(self, owner, events, seg_offsets, status, ready=None):
         self._owner, self.events_raw, self.seg_offsets, self._status = owner, events, seg_offsets, status
         self._off_host = None
+        self._ready = ready   # CUDA event of the expand launch when it ran on the side stream (pipeline_depth 2)
+
+    def wait(self):
+        """Make the current stream wait for this step's expand (no-op unless the step was pipelined)."""
+        if self._ready is not None:
+            torch.cuda.current_stream().wait_event(self._ready)
+        return self
 
     # -- host-side accessors (synchronise) ----------------------------------------------------
     def offsets_host(self):
         if self._off_host is None:
+            self.wait()
             self._off_host = self.seg_offsets.cpu().numpy()
             self._owner.check_status()
         return self._off_host
@@ -120,6 +128,7 @@ class StepResult:
     def events(self):
         """int16 view [N, 4] of (x, y, t, p); x, y, t are uint16 bit patterns."""
         n = self.total_events()
+        self.wait()
         return self.events_raw[:n].view(torch.int16).view(-1, 4)
 
     def keys(self, flag_shift, data_shift, data_mask, stream=None):
@@ -154,7 +163,7 @@ class StepResult:
 
 class DVSStreams:
     def __init__(self, cfg: DVSConfig, device=None, event_capacity: Optional[int] = None,
-                 debug_planes: bool = False, force_generic: bool = False):
+                 debug_planes: bool = False, force_generic: bool = False, pipeline_depth: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("pydvs_b200 needs a CUDA device (there is no CPU path)")
         self.cfg = cfg = cfg.resolved()
@@ -195,19 +204,27 @@ class DVSStreams:
             if isinstance(row, torch.Tensor):
                 row = row.detach().cpu().numpy()
             self.lut = torch.from_numpy(np.ascontiguousarray(row, dtype=np.uint8)).to(dev)
-        # work buffers
+        # work buffers.  pipeline_depth 2 double-buffers everything K3 reads or writes, so that the expand of
+        # step n runs on a side stream while the tile pass of step n+1 already runs on the caller's stream.
         n_tiles = self.S * self.tps
-        self.records = torch.empty(n_tiles * self.tile_px, dtype=torch.int64, device=dev)
-        self.tile_counts = torch.zeros(self.S * self.C * self.tps, dtype=torch.int32, device=dev)
-        self.tile_excl = torch.zeros_like(self.tile_counts)
-        self.stream_totals = torch.zeros(self.S * self.C, dtype=torch.int32, device=dev)
-        self.seg_offsets = torch.zeros(self.S * self.n_slots * 2 + 1, dtype=torch.int64, device=dev)
-        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.redo = torch.zeros(1 + n_tiles, dtype=torch.int32, device=dev)
         if event_capacity is None:
             event_capacity = max(1024, (self.S * self.P) // 2)
         self.event_capacity = int(event_capacity)
-        self.events = torch.empty(self.event_capacity, dtype=torch.int64, device=dev)
+        self.pipeline_depth = max(1, int(pipeline_depth))
+
+        def make_set():
+            counts = torch.zeros(self.S * self.C * self.tps, dtype=torch.int32, device=dev)
+            return {"records": torch.empty(n_tiles * self.tile_px, dtype=torch.int64, device=dev),
+                    "tile_counts": counts, "tile_excl": torch.zeros_like(counts),
+                    "stream_totals": torch.zeros(self.S * self.C, dtype=torch.int32, device=dev),
+                    "seg_offsets": torch.zeros(self.S * self.n_slots * 2 + 1, dtype=torch.int64, device=dev),
+                    "events": torch.empty(self.event_capacity, dtype=torch.int64, device=dev), "k3_done": None}
+
+        self._sets = [make_set() for _ in range(self.pipeline_depth)]
+        self._cur = 0
+        self._side = torch.cuda.Stream(device=dev) if self.pipeline_depth > 1 else None
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.redo = torch.zeros(1 + n_tiles, dtype=torch.int32, device=dev)
         self.debug = None
         if debug_planes:
             self.debug = {n: torch.zeros((self.S, self.H, self.W), dtype=torch.int16, device=dev)
@@ -216,6 +233,14 @@ class DVSStreams:
         self._enc = self._make_enc()
         self._params = self._make_params()
         self.frames_done = 0
+
+    # the buffer set of the most recent step
+    records = property(lambda self: self._sets[self._cur]["records"])
+    tile_counts = property(lambda self: self._sets[self._cur]["tile_counts"])
+    tile_excl = property(lambda self: self._sets[self._cur]["tile_excl"])
+    stream_totals = property(lambda self: self._sets[self._cur]["stream_totals"])
+    seg_offsets = property(lambda self: self._sets[self._cur]["seg_offsets"])
+    events = property(lambda self: self._sets[self._cur]["events"])
 
     # -- parameter blocks ---------------------------------------------------------------------
     def _make_enc(self):
@@ -241,8 +266,7 @@ class DVSStreams:
         p.thr = self.thr.data_ptr() if self.thr is not None else None
         if self.debug:
             p.diff_out, p.abs_diff_out, p.spikes_out = (self.debug[n].data_ptr() for n in ("diff", "abs_diff", "spikes"))
-        p.records, p.tile_counts, p.status = self.records.data_ptr(), self.tile_counts.data_ptr(), self.status.data_ptr()
-        p.redo = self.redo.data_ptr()
+        p.status, p.redo = self.status.data_ptr(), self.redo.data_ptr()   # records / tile_counts: set per step
         return p
 
     # -- the hot path -------------------------------------------------------------------------
@@ -254,17 +278,45 @@ class DVSStreams:
             raise ValueError("frames must be a CUDA tensor of dtype %s" % want)
         if frames.numel() != self.S * self.P or not frames.is_contiguous():
             raise ValueError("frames must be contiguous with shape [%d, %d, %d]" % (self.S, self.H, self.W))
+        self.begin_step()
         self.tile_pass(frames)
         self.scan()
-        if expand:
-            self.expand()
-        self.frames_done += 1
-        return StepResult(self, self.events, self.seg_offsets, self.status)
+        ready = self.expand_async() if expand else None
+        return StepResult(self, self.events, self.seg_offsets, self.status, ready)
 
-    # the three launches of a step, individually (bench.py times K1 on its own)
+    # the launches of a step, individually (bench.py times K1 on its own)
+    def begin_step(self):
+        """Select the buffer set of the new step; when pipelined, wait for the expand that last used it."""
+        self._cur = self.frames_done % self.pipeline_depth
+        self.frames_done += 1
+        done = self._sets[self._cur]["k3_done"]
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
+
+    def expand_async(self):
+        """K3 on the side stream when pipeline_depth > 1 (returns the event to wait on), else in line."""
+        if self._side is None:
+            self.expand()
+            return None
+        fork = torch.cuda.Event()
+        fork.record()
+        self._side.wait_event(fork)
+        with torch.cuda.stream(self._side):
+            self.expand()
+            done = torch.cuda.Event()
+            done.record()
+        self._sets[self._cur]["k3_done"] = done
+        return done
+
+    def drain(self):
+        """Make the current stream wait for every outstanding side-stream expand."""
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+
     def tile_pass(self, frames):
         """K1: fused threshold / inhibition / state update / record compaction / slot counts."""
         self._params.curr = frames.data_ptr()
+        self._params.records, self._params.tile_counts = self.records.data_ptr(), self.tile_counts.data_ptr()
         check(lib.dvs_step_fused(C.byref(self._params), current_stream_ptr()))
 
     def scan(self):
@@ -277,9 +329,10 @@ class DVSStreams:
         """Capture one step (all launches) reading from the static buffer ``frames`` into a CUDA graph.
         Copy each new frame into ``frames`` and call ``replay()``: one graph launch instead of six
         launches from Python (128x128 / 640x480 single streams are launch-bound)."""
+        if self.pipeline_depth != 1:
+            raise ValueError("graph capture uses the single-buffered pipeline (pipeline_depth=1)")
         self.step(frames)          # warm-up outside the capture: function attributes, lazy module load
         torch.cuda.synchronize()
-        self.ref_snapshot = None
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             self.tile_pass(frames)
@@ -300,8 +353,10 @@ class DVSStreams:
 
     def grow_events(self, capacity):
         """Re-allocate the event buffer and redo the expand of the last step (records are kept)."""
+        self.drain()
         self.event_capacity = int(capacity)
-        self.events = torch.empty(self.event_capacity, dtype=torch.int64, device=self.device)
+        for st in self._sets:
+            st["events"] = torch.empty(self.event_capacity, dtype=torch.int64, device=self.device)
         self.status.zero_()
         self.expand()
         return StepResult(self, self.events, self.seg_offsets, self.status)

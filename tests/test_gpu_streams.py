@@ -254,6 +254,25 @@ def test_fast_adaptive_kernel_declines_out_of_range_tiles():
     _run_case(1, 8, 1920, output_type="RATE", adaptive=True, inh=2, source="wide", frames=3, thr0=12, debug=False)
 
 
+def test_pipelined_expand_matches_in_line_expand():
+    """pipeline_depth 2: the expand of step n runs on a side stream, double-buffered against step n+1."""
+    from pydvs_b200 import DVSConfig, DVSStreams, synth
+    cfg = DVSConfig(width=1920, height=64, streams=3, output_type="RATE", inh_area_width=2)
+    a, b = DVSStreams(cfg), DVSStreams(cfg, pipeline_depth=2)
+    pending = []
+    for t in range(7):
+        f = synth.moving_bar(3, 64, 1920, t, noise=10, seed=4) if t % 3 else synth.random_frames(3, 64, 1920, t)
+        ra, rb = a.step(f), b.step(f)
+        pending.append((ra.seg_offsets.clone(), ra.events().clone(), rb))
+        if len(pending) == 2:                      # consume one step late, like a streaming consumer would
+            off, ev, late = pending.pop(0)
+            assert torch.equal(off, late.wait().seg_offsets) and torch.equal(ev, late.events())
+        assert torch.equal(a.ref, b.ref)
+    b.drain()
+    off, ev, late = pending.pop(0)
+    assert torch.equal(off, late.seg_offsets) and torch.equal(ev, late.events())
+
+
 def test_cuda_graph_replay_matches_eager_steps():
     from pydvs_b200 import DVSConfig, DVSStreams, synth
     cfg = DVSConfig(width=128, height=128, streams=1, output_type="RATE", inh_area_width=2)
