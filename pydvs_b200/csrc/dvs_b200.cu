@@ -245,12 +245,13 @@ __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ ExpandAr
           const int i = i0 + 32 * u + lane;
           const uint2 r = rr[u];
           int desc = (A.enc.mode == DVS_ENC_TIME) ? -1 : 0;
-          if (i < n) desc = enc_desc(A.enc, (int)(short)(r.y & 0xffff), pol == 0, status);
+          if (i < n) desc = (r.y >> 16) ? (int)(r.y >> 16) - 2 : enc_desc(A.enc, (int)(short)(r.y & 0xffff), pol == 0, status);
           const uint32_t xy = (r.x >> 16) | (r.x << 16);  // record is (row, col); event is (x = col, y = row)
           const int dmax = __reduce_max_sync(kFull, desc);
           if (A.enc.mode == DVS_ENC_RATE && dmax <= 0) continue;  // nothing in this chunk emits
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            if (A.enc.mode == DVS_ENC_RATE ? j >= dmax : j > dmax) break;  // no record of the chunk reaches slot j
             const bool m = (A.enc.mode == DVS_ENC_RATE) ? desc > j : desc == j;
             const unsigned bal = __ballot_sync(kFull, m);
             if (m) *reinterpret_cast<uint2 *>(ev_s + base[j] + __popc(bal & lt)) = make_uint2(xy, (uint32_t)j | pbits);

@@ -210,15 +210,16 @@ __global__ void __launch_bounds__(256, 4) k_tile_fast(const __grid_constant__ Ti
       if (win) {
         const int upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;  // update_reference_rate gs:244-249
         ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
+        int desc = 0;
         if (SIMPLE) {
           tp = !neg; tn = neg;
-          const int k = max(0, (A.enc.n_slots - 1) - (int)__umulhi((unsigned)a, A.enc.dv.magic));  // gs:830-832
-          if (k < 8) { if (tp) hp += 1ull << (8 * k); else hn += 1ull << (8 * k); }
+          desc = max(0, (A.enc.n_slots - 1) - (int)__umulhi((unsigned)a, A.enc.dv.magic));  // k, gs:830-832
+          if (desc < 8) { if (tp) hp += 1ull << (8 * desc); else hn += 1ull << (8 * desc); }
         } else {
           split_px(neg ? -1 : 1, A.polarity, A.uncoded, tp, tn);
-          if (tp || tn) hist_add(A, hist, nh, a, tp, hp, hn, status);
+          if (tp || tn) desc = hist_add(A, hist, nh, a, tp, hp, hn, status);
         }
-        rec = make_uint2((uint32_t)(row0 + y) | ((uint32_t)x << 16), (uint32_t)a);
+        rec = make_uint2((uint32_t)(row0 + y) | ((uint32_t)x << 16), rec_word1(a, desc, A.enc.mode != DVS_ENC_NONE));
       }
     }
     const unsigned bp = __ballot_sync(kFull, tp), bn = __ballot_sync(kFull, tn);
@@ -531,15 +532,16 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
         else upd = (int)__ldg(A.upd.lut + idx) * (A.upd.mode == DVS_UPD_TIME_BIN_THR ? T : 1);
       }
       ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
+      int desc = 0;
       if (SIMPLE) {
         tp = !neg; tn = neg;
-        const int k = max(0, (A.enc.n_slots - 1) - (int)__umulhi((unsigned)a, A.enc.dv.magic));  // gs:830-832
-        atomicAdd(&hist[(neg ? nh : 0) + k], 1u);  // fire-and-forget shared-memory reduction (k <= n_slots - 1)
+        desc = max(0, (A.enc.n_slots - 1) - (int)__umulhi((unsigned)a, A.enc.dv.magic));  // k, gs:830-832
+        atomicAdd(&hist[(neg ? nh : 0) + desc], 1u);  // fire-and-forget shared-memory reduction (k <= n_slots - 1)
       } else {
         split_px(neg ? -1 : 1, A.polarity, A.uncoded, tp, tn);
-        if (tp || tn) hist_add(A, hist, nh, a, tp, hp, hn, status, /*allow_regs=*/false);
+        if (tp || tn) desc = hist_add(A, hist, nh, a, tp, hp, hn, status, /*allow_regs=*/false);
       }
-      rec = make_uint2((uint32_t)(row0 + y) | ((uint32_t)x << 16), (uint32_t)a);
+      rec = make_uint2((uint32_t)(row0 + y) | ((uint32_t)x << 16), rec_word1(a, desc, A.enc.mode != DVS_ENC_NONE));
     }
     const unsigned bp = __ballot_sync(kFull, tp), bn = __ballot_sync(kFull, tn);
     if (tp) rec_sm[lo + w_pos + __popc(bp & lt)] = rec;

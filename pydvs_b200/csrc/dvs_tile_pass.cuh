@@ -80,10 +80,8 @@ DEV uint32_t sgn_code(int s) { return s > 0 ? 1u : (s < 0 ? 2u : 0u); }
 // One record's contribution to the tile's per-slot event counts.  fast_hist (RATE / TIME with
 // n_slots <= 8): 8-bit fields of two 64-bit registers per thread (callers add < 256 records per
 // thread between flushes); otherwise shared-memory atomics.
-DEV void hist_add(const TileArgs &A, uint32_t *hist, int nh, int a, bool tp, unsigned long long &hp,
-                  unsigned long long &hn, unsigned &status, bool allow_regs = true) {
-  if (A.enc.mode == DVS_ENC_NONE) return;
-  const int desc = enc_desc(A.enc, a, tp, status);
+DEV void hist_add_desc(const TileArgs &A, uint32_t *hist, int nh, int desc, bool tp, unsigned long long &hp,
+                       unsigned long long &hn, unsigned &status, bool allow_regs = true) {
   if (A.fast_hist && allow_regs) {  // desc in [-1, 8]
     if (desc >= 0 && desc < 8) {
       if (tp) hp += 1ull << (8 * desc); else hn += 1ull << (8 * desc);
@@ -99,6 +97,21 @@ DEV void hist_add(const TileArgs &A, uint32_t *hist, int nh, int a, bool tp, uns
       if (m) atomicAdd(&hist[(tp ? 0 : nh) + jj], (unsigned)m);
     }
   }
+}
+
+// Returns the record's encoder descriptor (enc_desc) so that callers can store it with the record.
+DEV int hist_add(const TileArgs &A, uint32_t *hist, int nh, int a, bool tp, unsigned long long &hp,
+                 unsigned long long &hn, unsigned &status, bool allow_regs = true) {
+  if (A.enc.mode == DVS_ENC_NONE) return 0;
+  const int desc = enc_desc(A.enc, a, tp, status);
+  hist_add_desc(A, hist, nh, desc, tp, hp, hn, status, allow_regs);
+  return desc;
+}
+
+// Records carry their encoder descriptor in the upper half of the second word as desc + 2 (0 = absent), so
+// that the expand kernel does not have to redo the division / table look-up.
+DEV uint32_t rec_word1(int a, int desc, bool has_desc) {
+  return (uint32_t)(a & 0xffff) | (has_desc ? (uint32_t)(desc + 2) << 16 : 0u);
 }
 
 // Flush the register histograms into the shared-memory histogram (one redux.sync per pair of bins) and
@@ -216,10 +229,10 @@ DEV void tile_compact(const TileArgs &A, int tile, int s_idx, int t_idx, int row
         const bool tp = (posm[j] >> p) & 1u, tn = (negm[j] >> p) & 1u;
         if (tp || tn) {
           const int a = get16(a_pk[j], p);
-          const uint2 rec = make_uint2((uint32_t)y | ((uint32_t)x << 16), (uint32_t)(a & 0xffff));
+          const int desc = hist_add(A, hist, nh, a, tp, hp, hn, status);
+          const uint2 rec = make_uint2((uint32_t)y | ((uint32_t)x << 16), rec_word1(a, desc, A.enc.mode != DVS_ENC_NONE));
           if (tp) *reinterpret_cast<uint2 *>(pos_dst + op++) = rec;
           else *reinterpret_cast<uint2 *>(neg_dst + on++) = rec;
-          hist_add(A, hist, nh, a, tp, hp, hn, status);
         }
         if (++x == A.W) { x = 0; ++y; }
       }
