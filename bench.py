@@ -467,7 +467,7 @@ def run_ours(args, wl, rank, local_rank, world):
                    "adaptive_threshold": wl["adaptive"], "pattern": args.pattern, "frame_dtype": args.frame_dtype,
                    "ring_frames": args.ring, "settle_steps": args.settle, "pipeline_depth": depth, "l2": "inputs larger than L2 (%.1f GB touched per step)" % (step_bytes / 1e9),
                    "events_last_step": events_last_step, "tile_rows": dvs.tile_rows},
-        "roofline": {"bound": "hbm", "kernel": "k_tile_pass (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "K1 fused tile pass (k_tile_fast2 when the fast path applies; timed with its 4-byte memset and the normally empty k_tile_redo launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "frac_of_8tbs_spec": achieved / 8000.0, "bytes_per_px": bytes_px, "k1_ms": k1_ms,
                      "scan_expand_ms": rest_ms, "k1_share_of_step": k1_ms / (k1_ms + rest_ms),
