@@ -629,7 +629,7 @@ int dvs_get_limits(dvs_limits *out) {
 int dvs_choose_tile_rows(int32_t S, int32_t H, int32_t W, int32_t inh_k) {
   const int k = inh_k > 1 ? inh_k : 1;
   if (S <= 0 || H <= 0 || W <= 0 || (long long)W * k > kMaxTilePx) return -1;
-  if (k == 2 && W >= 1024 && W % 8 == 0 && H % 2 == 0) return 2;  // 2x2 areas stay inside one thread (k_tile_fast2)
+  if (k == 2 && W % 8 == 0 && H % 2 == 0 && W >= 64) return 2;  // 2x2 areas stay inside one thread (k_tile_fast2)
   const int target_px = 8192;
   int rows = (target_px / W) / k * k;
   if (rows < k) rows = k;
@@ -697,12 +697,12 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
   // (the register-only kernels also take 0 <= history_weight < 1 and the time-binary updates)
   const bool plain = p->update_mode == DVS_UPD_RATE && p->history_weight == 1.0;
   const bool regs_only = k == 1 || (k == 2 && A.tile_rows == 2 && A.H % 2 == 0);
-  const bool upd_ok = plain || (regs_only && p->history_weight >= 0.0 && p->history_weight <= 1.0 &&
-                                (p->update_mode == DVS_UPD_RATE || p->update_mode == DVS_UPD_TIME_BIN_RAW ||
-                                 (p->update_mode == DVS_UPD_TIME_BIN_THR && p->threshold <= 128)));
+  const bool upd_ok = regs_only && (plain || (p->history_weight >= 0.0 && p->history_weight <= 1.0 &&
+                                             (p->update_mode == DVS_UPD_RATE || p->update_mode == DVS_UPD_TIME_BIN_RAW ||
+                                              (p->update_mode == DVS_UPD_TIME_BIN_THR && p->threshold <= 128))));
   const bool fast = !p->adaptive && upd_ok &&
                     p->threshold >= 2 && p->threshold <= 32767 && p->max_time_ms >= 0 && A.vec_ok &&
-                    A.W % 8 == 0 && A.tile_px / 8 <= 1024 && k <= 2 && !p->diff_out && !p->abs_diff_out &&
+                    A.W % 8 == 0 && A.tile_px / 8 <= 1024 && !p->diff_out && !p->abs_diff_out &&
                     !p->spikes_out && !p->force_generic && p->redo && A.S <= 65535;
   A.redo = p->redo;
   if (fast) return u8 ? launch_tile_fast_u8(A, st) : launch_tile_fast_i16(A, st);

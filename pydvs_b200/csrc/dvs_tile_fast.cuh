@@ -1,18 +1,19 @@
-// dvs_tile_fast.cuh -- K1 fast path: static threshold T >= 2, update_reference_rate, history_weight == 1.
+// dvs_tile_fast.cuh -- K1 fast path: static threshold T >= 2 or the adaptive-threshold plane, rate / time-binary
+// update, history_weight in [0, 1], inhibition off or 2x2 (two-row tiles).
 //
 // Same contract and bit-exact results as the generic tile pass (dvs_tile_pass.cuh); the difference is
 // instruction count.  When every frame / reference pixel of a tile is in [0, 255] (a block-wide vote;
-// otherwise the tile falls back to the generic body) nothing can wrap in 16 bits, so
-//   1. |frame - ref|, the threshold test and the sign run on packed u16x2 lanes with DPX min/max
-//      (VIMNMX.U16x2), ~8 instructions per 2 pixels with no unpacking; the signed, thresholded
-//      difference of every pixel goes to shared memory;
-//   2. a tile without a spike (one block-wide vote) only zeroes its counters; with history_weight == 1
-//      the reference of a pixel that does not spike is unchanged (clip(r + 0, 0, 255) == r), so quiet
-//      pixels are never written back;
-//   3. the spiking pixels of the tile are compacted IN ROW-MAJOR ORDER into a shared-memory work list
-//      (shuffle scans), and everything that is expensive per spike -- 2x2 inhibition arg-max, reference
-//      update, list membership, slot histogram, record emission -- runs one spike per lane with
-//      ballot/popc ranks, i.e. cost proportional to the number of spikes, not of pixels.
+// otherwise the tile is handed to the generic body through the redo list) nothing can wrap in 16 bits, so
+//   1. |frame - ref| and the threshold test run on packed u16x2 lanes with DPX min/max (VIMNMX.U16x2),
+//      ~5 instructions per 2 pixels with no unpacking; with two-row tiles each thread owns the same column
+//      blocks in both rows, so the 2x2 inhibition arg-max is taken in registers right there;
+//   2. with history_weight == 1 the reference of a pixel that does not spike is unchanged
+//      (clip(r + 0, 0, 255) == r): quiet pixels are never written back, quiet tiles only zero their counters;
+//   3. the surviving spikes of the tile are compacted IN ROW-MAJOR ORDER into a shared-memory work list
+//      (shuffle scans over packed counters, one barrier), and everything that is expensive per spike --
+//      reference update, list membership, slot histogram (fire-and-forget shared-memory atomics), record --
+//      runs one spike per lane with ballot/popc ranks: cost proportional to the number of spikes, spread evenly
+//      over the lanes, not to the number of pixels.
 #pragma once
 #include "dvs_tile_pass.cuh"
 
@@ -26,236 +27,6 @@ DEV uint4 ld16_stream(const void *p) { return __ldcs(reinterpret_cast<const uint
 #define FAST2_MINB 5
 #endif
 constexpr int kFastCap = 2048;  // work-list capacity; denser tiles go to the generic body (redo list)
-
-// shared memory: [sd: tile_px int16][wl: kFastCap u32][rec: kFastCap uint2][wtot: 128 u32]
-//                [hist: 2 * (n_slots + 1) u32]
-// SIMPLE: MERGED (or uncoded) list membership and the coded RATE encoder with <= 8 slots are inlined;
-// otherwise the shared split_px / hist_add helpers are used.  Grid: (tiles per stream, streams).
-template <int SRC, int J, int KI, bool SIMPLE>
-__global__ void __launch_bounds__(256, 4) k_tile_fast(const __grid_constant__ TileArgs A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int plane_bytes = (A.tile_px * 2 + 15) & ~15;
-  int16_t *sd_sm = reinterpret_cast<int16_t *>(smem_raw);
-  uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw + plane_bytes);
-  uint2 *rec_sm = reinterpret_cast<uint2 *>(smem_raw + plane_bytes + kFastCap * 4);
-  uint32_t *wtot = reinterpret_cast<uint32_t *>(smem_raw + plane_bytes + kFastCap * 12);
-  uint32_t *hist = wtot + 128;
-  const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
-  const int t_idx = blockIdx.x, s_idx = blockIdx.y;
-  const int tile = s_idx * A.tiles_per_stream + t_idx;
-  const int row0 = t_idx * A.tile_rows;
-  const int npx = min(A.tile_rows, A.H - row0) * A.W;  // multiple of 8 (host-checked)
-  const size_t plane_off = ((size_t)s_idx * A.H + row0) * A.W;
-  int16_t *const ref_t = A.ref + plane_off;
-  const unsigned char *const cur_t = static_cast<const unsigned char *>(A.curr) + plane_off * (SRC == SRC_U8 ? 1 : 2);
-
-  // ---- 1. loads: all 2 * J 128-bit requests of the thread are in flight before first use --------
-  uint32_t c_pk[J][4], r_pk[J][4];
-  bool have[J];
-#pragma unroll
-  for (int j = 0; j < J; ++j) {
-    const int q0 = (j * (int)blockDim.x + tid) * 8;
-    have[j] = q0 < npx;
-    if (have[j]) {
-      if (SRC == SRC_U8) {
-        const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(cur_t + q0));
-        c_pk[j][0] = __byte_perm(v.x, 0, 0x4140); c_pk[j][1] = __byte_perm(v.x, 0, 0x4342);
-        c_pk[j][2] = __byte_perm(v.y, 0, 0x4140); c_pk[j][3] = __byte_perm(v.y, 0, 0x4342);
-      } else {
-        const uint4 v = ld16_stream(cur_t + 2 * q0);
-        c_pk[j][0] = v.x; c_pk[j][1] = v.y; c_pk[j][2] = v.z; c_pk[j][3] = v.w;
-      }
-      const uint4 r = ld16(ref_t + q0);
-      r_pk[j][0] = r.x; r_pk[j][1] = r.y; r_pk[j][2] = r.z; r_pk[j][3] = r.w;
-    }
-  }
-  if (tid < 2 * nh) hist[tid] = 0;
-  for (int i = blockDim.x + tid; i < 2 * nh; i += blockDim.x) hist[i] = 0;
-
-  // ---- 2. packed threshold: a = max - min per u16 lane, spike iff a > T --------------------------
-  // Quiet groups (the common case) cost 4 instructions per 2 pixels plus one 128-bit shared store of
-  // zeros; sign and the 8-bit spike mask are only derived for groups that hold a spike.
-  const int T = A.thr_scalar;                                  // 2 <= T <= 32767 (host-checked)
-  const uint32_t kadd = (uint32_t)(0x7fff - T) * 0x00010001u;  // bit 15 of (a + kadd) <=> a > T
-  uint32_t flags8[J];
-  uint32_t rng = 0, cnt_lo = 0, cnt_hi = 0;  // counts of groups (0,1) and (2,3), 16-bit fields
-#pragma unroll
-  for (int j = 0; j < J; ++j) {
-    flags8[j] = 0;
-    if (!have[j]) continue;
-    const int q0 = (j * (int)blockDim.x + tid) * 8;
-    uint32_t a[4], fl[4], sd[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const uint32_t c = c_pk[j][w], r = r_pk[j][w];
-      a[w] = __vmaxu2(c, r) - __vminu2(c, r);  // no borrow: max >= min lane-wise
-      fl[w] = (a[w] + kadd) & 0x80008000u;       // spike flags at bits 15 / 31
-    }
-    rng |= (r_pk[j][0] | r_pk[j][1] | r_pk[j][2]) | r_pk[j][3];
-    if (SRC != SRC_U8) rng |= (c_pk[j][0] | c_pk[j][1] | c_pk[j][2]) | c_pk[j][3];
-    if (fl[0] | fl[1] | fl[2] | fl[3]) {
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const uint32_t c = c_pk[j][w], mn = __vminu2(c, r_pk[j][w]);
-        const uint32_t ne = ((mn ^ c) + 0x7fff7fffu) & 0x80008000u;  // lane of min differs from c <=> c > r
-        const uint32_t keep = (fl[w] >> 15) * 0xffffu;               // 0xffff in spiking lanes
-        const uint32_t neg = ((fl[w] & ~ne) >> 15) * 0xffffu;        // 0xffff in spiking lanes with c < r
-        // abs_diff * spikes, negated (two's complement per lane; a >= 3 there, so no carry) where c < r
-        sd[w] = ((a[w] & keep) ^ neg) + (neg & 0x00010001u);
-        flags8[j] |= (((fl[w] >> 15) & 1u) | ((fl[w] >> 30) & 2u)) << (2 * w);
-      }
-      const uint32_t n = __popc(flags8[j]);
-      if (j < 2) cnt_lo += n << (16 * (j & 1)); else cnt_hi += n << (16 * (j & 1));
-      // keep the group's signed differences for the work list (c_pk is dead from here on)
-      c_pk[j][0] = sd[0]; c_pk[j][1] = sd[1]; c_pk[j][2] = sd[2]; c_pk[j][3] = sd[3];
-    }
-    st16(sd_sm + q0, sd);
-  }
-
-  // ---- 3. ordered work list: exclusive scan of the spike counts in (group j, thread) order --------
-  // Warps without a spike skip their scan.  wtot[j * NW + warp] = count of (j, warp); wtot[96 + warp]
-  // carries the warp's "pixel outside [0, 255]" vote, so one barrier serves both.
-  const bool w_unsafe = __any_sync(kFull, (rng & 0xFF00FF00u) != 0);
-  const bool w_any = __any_sync(kFull, (cnt_lo | cnt_hi) != 0);
-  uint32_t in_lo = cnt_lo, in_hi = cnt_hi;
-  if (w_any) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y0 = __shfl_up_sync(kFull, in_lo, o), y1 = __shfl_up_sync(kFull, in_hi, o);
-      if (lane >= o) { in_lo += y0; in_hi += y1; }
-    }
-  }
-  if (lane == 31) {
-    wtot[0 * NW + warp] = in_lo & 0xffff;
-    if (J > 1) { wtot[1 * NW + warp] = in_lo >> 16; wtot[2 * NW + warp] = in_hi & 0xffff; wtot[3 * NW + warp] = in_hi >> 16; }
-    wtot[96 + warp] = w_unsafe ? 1u : 0u;
-  }
-  __syncthreads();
-  // every warp scans the <= 32 (j, warp) totals redundantly: no second barrier
-  const uint32_t ent = lane < J * NW ? wtot[lane] : 0u;
-  uint32_t ent_in = ent;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t y = __shfl_up_sync(kFull, ent_in, o);
-    if (lane >= o) ent_in += y;
-  }
-  const int n_cand = (int)__shfl_sync(kFull, ent_in, 31);
-  const bool unsafe = __any_sync(kFull, lane < NW && wtot[96 + lane] != 0);
-  if (n_cand == 0 && !unsafe) {  // quiet tile: no records, no events, reference untouched
-    for (int c = tid; c < A.C; c += blockDim.x)
-      A.tile_counts[((size_t)s_idx * A.C + c) * A.tiles_per_stream + t_idx] = 0;
-    return;
-  }
-  if (unsafe || n_cand > kFastCap) {  // generic body: exact int16 wrap semantics / dense tiles
-    if (tid == 0) A.redo[1 + atomicAdd(A.redo, 1)] = tile;
-    return;
-  }
-  {
-    // work-list entry: tile-local pixel index (13 bits) | reference value << 13 (8 bits) |
-    //                  abs_diff << 21 (8 bits) | negative << 29
-    const uint32_t ent_ex = ent_in - ent;
-    const uint32_t ex_lo = in_lo - cnt_lo, ex_hi = in_hi - cnt_hi;  // lane-exclusive, 16-bit fields
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const uint32_t base = __shfl_sync(kFull, ent_ex, j * NW + warp);
-      if (flags8[j] == 0) continue;
-      const int q0 = (j * (int)blockDim.x + tid) * 8;
-      uint32_t pos = base + (((j < 2 ? ex_lo : ex_hi) >> (16 * (j & 1))) & 0xffffu);
-#pragma unroll
-      for (int p = 0; p < 8; ++p)
-        if ((flags8[j] >> p) & 1u) {
-          const int v = get16(c_pk[j], p);
-          wl[pos++] = (uint32_t)(q0 + p) | ((uint32_t)get16(r_pk[j], p) << 13) |
-                      ((uint32_t)(v < 0 ? -v : v) << 21) | (v < 0 ? 1u << 29 : 0u);
-        }
-    }
-  }
-  __syncthreads();
-
-  // ---- 4a. one spiking pixel per lane: inhibition, reference update, list membership, histogram.
-  // Records are staged in shared memory, compacted inside the warp's own slice [lo, hi) of the work
-  // list: pos records forwards from lo, neg records backwards from hi - 1.
-  const int per_warp = (((n_cand + NW - 1) / NW) + 31) & ~31;
-  const int lo = min(n_cand, warp * per_warp), hi = min(n_cand, lo + per_warp);
-  const unsigned magic = A.upd.div_thr.magic;
-  const int max_n = A.upd.max_time_ms;
-  const unsigned lt = (1u << lane) - 1u;
-  unsigned long long hp = 0, hn = 0;
-  unsigned status = 0;
-  uint32_t w_pos = 0, w_neg = 0;
-  for (int i0 = lo; i0 < hi; i0 += 32) {
-    const int i = i0 + lane;
-    bool tp = false, tn = false;
-    uint2 rec = make_uint2(0u, 0u);
-    if (i < hi) {
-      const uint32_t e = wl[i];
-      const int q = e & 0x1fff, r = (e >> 13) & 0xff, a = (e >> 21) & 0xff;
-      const bool neg = (e >> 29) & 1u;
-      const int y = (int)__umulhi((unsigned)q, A.inv_w), x = q - y * A.W;
-      bool win = true;
-      if (KI == INH_K2) {  // local_inhibition gs:177-221: first arg-max of the 2x2 area, row-major, strict '>'
-        const int o = (y & ~1) * A.W + (x & ~1);
-        const uint32_t top = *reinterpret_cast<const uint32_t *>(sd_sm + o);
-        const uint32_t bot = *reinterpret_cast<const uint32_t *>(sd_sm + o + A.W);
-        const int t00 = abs((int)(short)(top & 0xffff)), t01 = abs((int)(short)(top >> 16));
-        const int t10 = abs((int)(short)(bot & 0xffff)), t11 = abs((int)(short)(bot >> 16));
-        int best = t00, bi = 0;
-        if (t01 > best) { best = t01; bi = 1; }
-        if (t10 > best) { best = t10; bi = 2; }
-        if (t11 > best) { best = t11; bi = 3; }
-        win = bi == (((y & 1) << 1) | (x & 1));
-      }
-      if (win) {
-        const int upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;  // update_reference_rate gs:244-249
-        ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
-        int desc = 0;
-        if (SIMPLE) {
-          tp = !neg; tn = neg;
-          desc = max(0, (A.enc.n_slots - 1) - (int)__umulhi((unsigned)a, A.enc.dv.magic));  // k, gs:830-832
-          if (desc < 8) { if (tp) hp += 1ull << (8 * desc); else hn += 1ull << (8 * desc); }
-        } else {
-          split_px(neg ? -1 : 1, A.polarity, A.uncoded, tp, tn);
-          if (tp || tn) desc = hist_add(A, hist, nh, a, tp, hp, hn, status);
-        }
-        rec = make_uint2((uint32_t)(row0 + y) | ((uint32_t)x << 16), rec_word1(a, desc, A.enc.mode != DVS_ENC_NONE));
-      }
-    }
-    const unsigned bp = __ballot_sync(kFull, tp), bn = __ballot_sync(kFull, tn);
-    if (tp) rec_sm[lo + w_pos + __popc(bp & lt)] = rec;
-    if (tn) rec_sm[hi - 1 - (w_neg + __popc(bn & lt))] = rec;
-    w_pos += __popc(bp);
-    w_neg += __popc(bn);
-    // kFastCap / NW rounded up to 32 -> at most 8 records per lane: the 8-bit histogram fields are safe
-  }
-  if (lane == 0) wtot[64 + warp] = w_pos | (w_neg << 16);
-  hist_flush(A, hist, nh, hp, hn, status);  // before the barrier: counters can then be written without another one
-  __syncthreads();
-  uint32_t base = 0, totals = 0;
-  {
-    const uint32_t t = lane < NW ? wtot[64 + lane] : 0u;
-    uint32_t t_in = t;
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {  // NW <= 8
-      const uint32_t y = __shfl_up_sync(kFull, t_in, o);
-      if (lane >= o) t_in += y;
-    }
-    base = __shfl_sync(kFull, t_in - t, warp);
-    totals = __shfl_sync(kFull, t_in, 7);
-  }
-  const int n_pos_tile = totals & 0xffff, n_neg_tile = totals >> 16;
-
-  // ---- 4b. coalesced copy of the warp's staged records to their ranks in the tile's lists ----------
-  if (w_pos | w_neg) {
-    const size_t region = (size_t)tile * A.tile_px;
-    dvs_record *pos_dst = A.records + region + (base & 0xffff);
-    dvs_record *neg_dst = A.records + region + (A.tile_px - n_neg_tile) + (base >> 16);
-    for (int i = lane; i < (int)w_pos; i += 32) *reinterpret_cast<uint2 *>(pos_dst + i) = rec_sm[lo + i];
-    for (int i = lane; i < (int)w_neg; i += 32) *reinterpret_cast<uint2 *>(neg_dst + i) = rec_sm[hi - 1 - i];
-  }
-  write_counters(A, s_idx, t_idx, hist, nh, n_pos_tile, n_neg_tile);
-}
 
 // ---- fast kernel, register-only variant ---------------------------------------------------------
 // Used when no shared-memory plane is needed: inhibition off (PAIR == false: thread owns JH groups in
@@ -580,32 +351,6 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
   write_counters(A, s_idx, t_idx, hist, nh, n_pos_tile, n_neg_tile);
 }
 
-template <int SRC, int J, int KI, bool SIMPLE>
-static int launch_fast_shape(const TileArgs &A, int bd, size_t smem, cudaStream_t st) {
-  auto k = k_tile_fast<SRC, J, KI, SIMPLE>;
-  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
-  }
-  cudaError_t e = cudaMemsetAsync(A.redo, 0, sizeof(int32_t), st);
-  if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
-  const long long tiles = (long long)A.S * A.tiles_per_stream;
-  k<<<dim3((unsigned)A.tiles_per_stream, (unsigned)A.S), bd, smem, st>>>(A);
-  if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
-  // generic body over the (normally zero) tiles with pixels outside [0, 255]
-  auto kr = k_tile_redo<SRC, J, KI>;
-  const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
-  const size_t smem_r = ((KI != INH_NONE) ? ((A.tile_px * 2 + 15) & ~15) : 0) + (128 + 2 * nh + 8) * sizeof(uint32_t);
-  if (smem_r > 48 * 1024) {
-    e = cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
-    if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
-  }
-  kr<<<(unsigned)(tiles < 592 ? tiles : 592), bd, smem_r, st>>>(A);
-  if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
-  return DVS_OK;
-}
-
 template <int SRC, int JH, bool PAIR, bool SIMPLE, bool ADAPT = false>
 static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
   auto k = k_tile_fast2<SRC, JH, PAIR, SIMPLE, ADAPT>;
@@ -632,21 +377,17 @@ static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
   return DVS_OK;
 }
 
-// Caller guarantees: vec_ok, W % 8 == 0, <= 1024 groups per tile, inh_k in {1, 2}, 2 <= T, rate update,
-// history_weight == 1, max_time_ms >= 0, no debug planes.
+// Caller guarantees: vec_ok, W % 8 == 0, <= 1024 groups per tile, inhibition off or 2x2 on two-row tiles,
+// 2 <= T, rate or time-binary update, history_weight in [0, 1], max_time_ms >= 0, no debug planes.
 template <int SRC>
 static int dispatch_fast(const TileArgs &A, cudaStream_t st) {
   const int items = A.tile_px / 8;
-  const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
-  const bool k2 = A.inh_k == 2;
-  const size_t smem = (size_t)((A.tile_px * 2 + 15) & ~15) + kFastCap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t);
-  // inlined membership / histogram: MERGED or uncoded lists, coded RATE encoder, <= 8 slots, threshold >= 2
+  // inlined membership / histogram: MERGED lists, coded RATE encoder, <= 8 slots, plain rate update
   const bool simple = (A.uncoded == 0 && A.polarity == DVS_POL_MERGED) && A.enc.mode == DVS_ENC_RATE &&
                       A.enc.uncoded == 0 && A.enc.n_slots <= 8 && A.enc.n_slots >= 1 && A.enc.threshold >= 2 &&
                       A.enc.u16_vals == 0 && A.fast_hist && A.upd.mode == DVS_UPD_RATE && A.upd.hw_is_one;
   auto round32 = [](int x) { return (x + 31) / 32 * 32; };
-  // register-only variant: no inhibition, or 2x2 inhibition on two-row tiles
-  if (!k2) {
+  if (A.inh_k != 2) {
     if (items <= 256) {
       const int bd = round32(items);
       return simple ? launch_fast2<SRC, 1, false, true>(A, bd, st) : launch_fast2<SRC, 1, false, false>(A, bd, st);
@@ -654,21 +395,13 @@ static int dispatch_fast(const TileArgs &A, cudaStream_t st) {
     const int bd = round32((items + 3) / 4);
     return simple ? launch_fast2<SRC, 4, false, true>(A, bd, st) : launch_fast2<SRC, 4, false, false>(A, bd, st);
   }
-  if (k2 && A.tile_rows == 2 && A.H % 2 == 0) {
-    const int gpr = A.W / 8;
-    if (gpr <= 256) {
-      const int bd = round32(gpr);
-      return simple ? launch_fast2<SRC, 1, true, true>(A, bd, st) : launch_fast2<SRC, 1, true, false>(A, bd, st);
-    }
-    const int bd = round32((gpr + 1) / 2);
-    return simple ? launch_fast2<SRC, 2, true, true>(A, bd, st) : launch_fast2<SRC, 2, true, false>(A, bd, st);
+  const int gpr = A.W / 8;  // two-row tiles: each thread owns the same column block(s) in both rows
+  if (gpr <= 256) {
+    const int bd = round32(gpr);
+    return simple ? launch_fast2<SRC, 1, true, true>(A, bd, st) : launch_fast2<SRC, 1, true, false>(A, bd, st);
   }
-  if (items <= 256) {
-    const int bd = round32(items);
-    return simple ? launch_fast_shape<SRC, 1, INH_K2, true>(A, bd, smem, st) : launch_fast_shape<SRC, 1, INH_K2, false>(A, bd, smem, st);
-  }
-  const int bd = round32((items + 3) / 4);
-  return simple ? launch_fast_shape<SRC, 4, INH_K2, true>(A, bd, smem, st) : launch_fast_shape<SRC, 4, INH_K2, false>(A, bd, smem, st);
+  const int bd = round32((gpr + 1) / 2);
+  return simple ? launch_fast2<SRC, 2, true, true>(A, bd, st) : launch_fast2<SRC, 2, true, false>(A, bd, st);
 }
 
 // Adaptive-threshold fast path.  Caller guarantees: vec_ok (incl. the threshold plane), W % 8 == 0,
