@@ -156,6 +156,15 @@ def test_many_slots_and_large_slot_counts():
     _run_case(1, 16, 32, output_type="TIME", num_bins=40, max_time_ms=40, frames=3, threshold=2)
 
 
+def test_degenerate_slot_counts():
+    for mt in (1, 2):   # rate coding with 1 or 2 lists: k = max(0, (max_time_ms - 1) - v) is (almost) always 0
+        _run_case(2, 16, 64, max_time_ms=mt, frames=3, debug=False, threshold=3)
+        _run_case(2, 16, 64, max_time_ms=mt, frames=3, debug=True, threshold=3)
+    _run_case(2, 16, 64, output_type="TIME", num_bins=1, frames=3, debug=False)
+    _run_case(1, 2, 8, frames=3, debug=False)            # a single tile of a single group pair
+    _run_case(1, 2, 8, inh=2, frames=3, debug=False)
+
+
 def test_wide_tile_variant():
     # W * inh_k > 8192 pixels per tile -> the 1024-thread generic variant
     _run_case(1, 8, 2064, inh=4, frames=3)
