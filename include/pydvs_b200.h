@@ -244,6 +244,78 @@ int dvs_move_mask_i16(const int16_t *images, int32_t n_images, const int32_t *im
                       const int32_t *dy, int32_t bg, const double *mask, int16_t *out, int32_t S, int32_t H,
                       int32_t W, void *stream);
 
+/* ---- rows either side of the path ---------------------------------------------- */
+
+/* Float32 NVS variants, pydvs/numba_nvs.py ("nvs").  One fused pass, in place on ref/thr (and the OFF
+ * cell), `spikes` overwritten, exactly the precision numba uses: float32 for thresholded_difference
+ * (nvs:6-20, NumPy floor_divide) and for array-only expressions, float64 with one rounding wherever a
+ * Python-float scalar enters (nvs:40, 52-60, 133-135).  The unseeded draws `uniform(0,1) <= p` of the
+ * noisy variants (nvs:85, 119, 133) are supplied by the caller as byte masks (non-zero = leak). */
+enum {
+  DVS_NVS_0 = 0,                      /* nvs_0 nvs:23-29                          */
+  DVS_NVS_LEAKY = 1,                  /* nvs_leaky nvs:32-40                      */
+  DVS_NVS_LEAKY_ADAPTIVE = 2,         /* nvs_leaky_adaptive nvs:43-60             */
+  DVS_NVS_NOISY_LEAKY_ADAPTIVE = 3,   /* nvs_noisy_leaky_adaptive nvs:64-90       */
+  DVS_NVS_BI_NOISY_LEAKY_ADAPTIVE = 4 /* nvs_bi_noisy_leaky_adaptive nvs:93-147   */
+};
+typedef struct dvs_nvs_params {
+  int32_t mode;              /* DVS_NVS_*                                                        */
+  int32_t reserved0;
+  int64_t n_px;              /* elements in every plane (any shape, any number of streams)       */
+  const float *frame;
+  float *ref, *thr, *spikes;
+  uint8_t *active;           /* optional: what thresholded_difference returns (0/1 per pixel)   */
+  const uint8_t *leak_mask;  /* modes 3, 4; NULL = no pixel leaks                                */
+  float *ref_off, *thr_off;  /* mode 4: the OFF cell                                             */
+  float *spikes_off;         /* mode 4, optional (a local in the reference)                      */
+  const uint8_t *leak_mask_off;
+  double reference_leak, threshold_base, threshold_mult_incr, threshold_leak, target_off;
+} dvs_nvs_params;
+int dvs_nvs_step_f32(const dvs_nvs_params *p, void *stream);
+
+/* Receiver, pydvs/decode_spikes.pyx ("dec").  ref_out = int16(ref * history_weight), the first
+ * statement of every update_ref_spike_list_* (dec:85, 121, 172). */
+int dvs_decay_i16(const int16_t *ref, int16_t *ref_out, double history_weight, int64_t n_px, void *stream);
+
+/* A batch of 16-bit keys (key_to_spike dec:46-67: row = key >> data_shift & mask, col = key & mask,
+ * sign = +1 when the flag bit is 0) for S streams of H x W pixels: the keys of stream s are
+ * keys[stream_offsets[s] .. stream_offsets[s+1]).  The reference call is S == 1. */
+typedef struct dvs_key_list {
+  const int16_t *keys;
+  const int64_t *stream_offsets; /* device, S + 1 entries */
+  int64_t n;
+  int32_t S, H, W;
+  int32_t flag_shift, data_shift, data_mask;
+} dvs_key_list;
+
+/* What the reference raises at an offending key; *first_error (device int32, initialise to
+ * DVS_DECODE_NO_ERROR) receives the smallest (key index << 2 | kind). */
+enum {
+  DVS_DECODE_KEY_NEGATIVE = 0, /* int16 key < 0 passed to a C uint16: OverflowError                 */
+  DVS_DECODE_INDEX = 1,        /* (row, col) outside the plane: undefined in the reference; skipped */
+  DVS_DECODE_VALUE_NAN = 2,    /* val_now is nan: ValueError                                        */
+  DVS_DECODE_VALUE_RANGE = 3   /* val_now does not fit int16: OverflowError                         */
+};
+#define DVS_DECODE_NO_ERROR 0x7f7f7f7f
+
+/* update_ref_spike_list_rate dec:71-94 after the decay: ref[row, col] += threshold * sign per key
+ * (int16 wrap; duplicates accumulate). */
+int dvs_decode_rate_i16(const dvs_key_list *keys, int16_t *ref, int32_t threshold, int32_t *first_error,
+                        void *stream);
+
+/* update_ref_spike_list_time dec:98-145 (binary == 0) / _time_bin dec:149-197 (binary == 1) after the
+ * decay, in place on ref / time_last / val_last.  The reference walks the keys sequentially; one call
+ * applies, for every pixel, the first key not yet applied (`done`, n bytes, zero before the first
+ * round) and counts the keys still waiting in *remaining: call again until it reads 0 (one round when
+ * no pixel repeats, as in every list the encoders produce).  `claim` is a S*H*W int32 scratch plane
+ * holding DVS_DECODE_NO_ERROR everywhere (memset 0x7f) on entry and on exit.  `log2_lut` (binary
+ * only): 32768 float64, log2_lut[v] = np.log2(v) for v >= 1, built by the host so that the values are
+ * NumPy's own. */
+int dvs_decode_time_round_i16(const dvs_key_list *keys, int32_t binary, int16_t *ref, int16_t *time_last,
+                              int16_t *val_last, const double *log2_lut, int32_t num_bins, double bin_width,
+                              int32_t time_period, uint32_t time_now, int32_t threshold, uint8_t *done,
+                              int32_t *claim, int32_t *remaining, int32_t *first_error, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -483,3 +483,182 @@ int orc_pipeline_frame(const orc_pipe_params *pp, const int16_t *curr, int16_t *
   if (rc) return rc;
   return orc_make_spike_lists(&pp->enc, pos, np_, P, neg, nn, P, slot_counts, out, out_cap, n_events);
 }
+
+/* ================================================================================================
+ * float NVS variants, pydvs/numba_nvs.py:6-147 (A.11).
+ * Arithmetic as numba types it [probed by running the reference under numba 0.65]:
+ *  - thresholded_difference (nvs:6-20) works on float32 arrays only -> float32 arithmetic; `//` is
+ *    NumPy's floor_divide (npy_divmodf: fmod, (a-mod)/b, sign fix-up, floor with the >0.5 snap);
+ *  - every expression that multiplies an array by one of the Python-float scalars (leaks, base,
+ *    increments, target) is evaluated in float64 and rounded to float32 once, on assignment;
+ *  - `reference += spikes` (nvs:29) and `reference * leak_active + spikes` (nvs:88,123: all float32
+ *    arrays) stay in float32.
+ * The noisy variants draw `uniform(0,1) <= p` from numba's private, unseeded RNG (nvs:85,119,133):
+ * not reproducible, so the draws are injected as byte masks (1 = leak this pixel).  p >= 1 / p < 0
+ * pin the two branches against the reference.
+ * ================================================================================================ */
+static float np_floor_dividef(float a, float b) {
+  if (b == 0.0f) return a / b;                       /* npy_divmodf: b == 0 -> a / b (inf or nan) */
+  float mod = fmodf(a, b);
+  float div = (a - mod) / b;
+  if (mod != 0.0f) {
+    if ((b < 0) != (mod < 0)) div -= 1.0f;
+  }
+  if (div != 0.0f) {
+    float fl = floorf(div);
+    if (div - fl > 0.5f) fl += 1.0f;
+    return fl;
+  }
+  return copysignf(0.0f, a / b);
+}
+
+/* nvs:6-20.  spikes <- discretised difference, returns activity in `active` (may be NULL). */
+static inline uint8_t nvs_td(float frame, float ref, float thr, float *spike) {
+  float d = frame - ref;                              /* nvs:13 */
+  uint8_t act = (uint8_t)(fabsf(d) >= thr);           /* nvs:14 (>=, not >); nan compares false */
+  d = d * (float)act;                                 /* nvs:15 */
+  *spike = np_floor_dividef(d, thr) * thr;            /* nvs:18 */
+  return act;
+}
+
+enum { NVS_0 = 0, NVS_LEAKY = 1, NVS_LEAKY_ADAPTIVE = 2, NVS_NOISY_LEAKY_ADAPTIVE = 3 };
+
+static inline float nvs_thr_update(float thr, uint8_t act, double base, double leak, double incr) {
+  double tb = (double)thr - base;                     /* nvs:52-55, left to right, float64 */
+  return (float)((base + tb * leak) + (tb * incr) * (double)act);
+}
+
+static inline float nvs_leak_active(uint8_t m, double ref_leak) {
+  /* nvs:85-86: ones(float32) += (draw <= p) * (reference_leak - 1): float64 sum, stored as float32 */
+  return (float)(1.0 + (double)m * (ref_leak - 1.0));
+}
+
+void orc_nvs_f32(int mode, const float *frame, float *ref, float *thr, float *spikes, uint8_t *active,
+                 const uint8_t *leak_mask, double ref_leak, double thr_base, double thr_incr,
+                 double thr_leak, long n) {
+  for (long i = 0; i < n; ++i) {
+    float sp;
+    uint8_t act = nvs_td(frame[i], ref[i], thr[i], &sp);
+    spikes[i] = sp;
+    if (active) active[i] = act;
+    if (mode == NVS_0) {                              /* nvs:23-29 */
+      ref[i] = ref[i] + sp;
+    } else if (mode == NVS_LEAKY) {                   /* nvs:32-40 */
+      ref[i] = (float)((double)ref[i] * ref_leak + (double)sp);
+    } else if (mode == NVS_LEAKY_ADAPTIVE) {          /* nvs:43-60 */
+      thr[i] = nvs_thr_update(thr[i], act, thr_base, thr_leak, thr_incr);
+      ref[i] = (float)((double)ref[i] * ref_leak + (double)sp);
+    } else {                                          /* nvs:64-90 */
+      thr[i] = nvs_thr_update(thr[i], act, thr_base, thr_leak, thr_incr);
+      float la = nvs_leak_active(leak_mask ? leak_mask[i] : 0, ref_leak);
+      ref[i] = ref[i] * la + sp;                      /* float32 arrays only */
+    }
+  }
+}
+
+/* nvs_bi_noisy_leaky_adaptive nvs:93-147: an ON cell (ref/thr) and an OFF cell (ref_off/thr_off);
+ * the OFF reference relaxes towards target_off starting from the *updated ON reference* (nvs:135). */
+void orc_nvs_bi_f32(const float *frame, float *ref, float *thr, float *spikes, float *ref_off,
+                    float *thr_off, float *spikes_off, const uint8_t *leak_mask,
+                    const uint8_t *leak_mask_off, double ref_leak, double thr_base, double thr_incr,
+                    double thr_leak, double target_off, long n) {
+  for (long i = 0; i < n; ++i) {
+    float sp, spo;
+    uint8_t act = nvs_td(frame[i], ref[i], thr[i], &sp);               /* nvs:107 */
+    uint8_t acto = nvs_td(frame[i], ref_off[i], thr_off[i], &spo);     /* nvs:108-109 */
+    spikes[i] = sp;
+    if (spikes_off) spikes_off[i] = spo;
+    thr[i] = nvs_thr_update(thr[i], act, thr_base, thr_leak, thr_incr);  /* nvs:111-114 */
+    float la = nvs_leak_active(leak_mask ? leak_mask[i] : 0, ref_leak);  /* nvs:117-120 */
+    ref[i] = ref[i] * la + sp;                                           /* nvs:121-123 */
+    thr_off[i] = nvs_thr_update(thr_off[i], acto, thr_base, thr_leak, thr_incr);  /* nvs:125-128 */
+    float lo = nvs_leak_active(leak_mask_off ? leak_mask_off[i] : 0, ref_leak);   /* nvs:130-132 */
+    ref_off[i] = (float)((target_off + ((double)ref[i] - target_off) * (double)lo) + (double)spo);  /* nvs:133-135 */
+  }
+}
+
+/* ================================================================================================
+ * receiver side, pydvs/decode_spikes.pyx:46-197.
+ * Keys are int16 arrays read into a C uint16 argument: a negative key raises OverflowError in the
+ * reference (-> rc 5).  The decoder uses the uncoded bit layout with flag bit 0 meaning +1 (B.12).
+ * ================================================================================================ */
+static inline void key_to_spike(uint16_t key, int flag_shift, int data_shift, int data_mask,
+                                int *row, int *col, int *sign) {
+  *row = (int16_t)((key >> data_shift) & data_mask);  /* dec:58 */
+  *col = (int16_t)(key & data_mask);                  /* dec:59 */
+  *sign = (((key >> flag_shift) & 1) == 0) ? 1 : -1;  /* dec:62-65 */
+}
+
+/* update_ref_spike_list_rate dec:71-94: ref_out = int16(ref*hw); then += threshold*sign per key.
+ * Out-of-image (row, col) is undefined behaviour in the reference (boundscheck off) -> rc 1. */
+int orc_decode_rate(const int16_t *ref, int16_t *ref_out, int H, int W, const int16_t *keys, long n,
+                    int threshold, double hw, int flag_shift, int data_shift, int data_mask) {
+  for (long i = 0; i < (long)H * W; ++i) ref_out[i] = hist(hw, ref[i]);  /* dec:85 */
+  for (long i = 0; i < n; ++i) {
+    if (keys[i] < 0) return 5;
+    int r, c, s;
+    key_to_spike((uint16_t)keys[i], flag_shift, data_shift, data_mask, &r, &c, &s);
+    if (r >= H || c >= W) return 1;
+    ref_out[(long)r * W + c] = w16((int32_t)ref_out[(long)r * W + c] + (int32_t)(int16_t)threshold * s);  /* dec:90 */
+  }
+  return 0;
+}
+
+/* float64 -> C int16 as Cython converts a NumPy float64 object: int(x) then range check.
+ * nan -> ValueError (rc 6), out of range / inf -> OverflowError (rc 5). */
+static int f64_to_i16(double v, int16_t *out) {
+  if (isnan(v)) return 6;
+  if (isinf(v)) return 5;
+  double t = trunc(v);
+  if (t < -32768.0 || t > 32767.0) return 5;
+  *out = (int16_t)t;
+  return 0;
+}
+
+static inline double py_mod(double a, double b) {     /* np.mod on floats: sign follows the divisor */
+  if (b == 0.0) return NAN;
+  double m = fmod(a, b);
+  if (m != 0.0) { if ((b < 0) != (m < 0)) m += b; } else m = copysign(0.0, b);
+  return m;
+}
+
+/* update_ref_spike_list_time dec:98-145 (binary == 0) and _time_bin dec:149-197 (binary == 1).
+ * In place on time_last / val_last (the reference mutates and returns them), ref_out is new. */
+int orc_decode_time(int binary, const int16_t *ref, int16_t *ref_out, int16_t *time_last,
+                    int16_t *val_last, int H, int W, const int16_t *keys, long n, int num_bins,
+                    double bin_width, int time_period, uint32_t time_now, int threshold, double hw,
+                    int flag_shift, int data_shift, int data_mask) {
+  for (long i = 0; i < (long)H * W; ++i) ref_out[i] = hist(hw, ref[i]);  /* dec:121 / dec:172 */
+  const int16_t thr = (int16_t)threshold, nb = (int16_t)num_bins, per = (int16_t)time_period;
+  for (long i = 0; i < n; ++i) {
+    if (keys[i] < 0) return 5;
+    int r, c, s;
+    key_to_spike((uint16_t)keys[i], flag_shift, data_shift, data_mask, &r, &c, &s);
+    if (r >= H || c >= W) return 1;
+    long q = (long)r * W + c;
+    if (val_last[q] == -1) {                          /* dec:128-133 / dec:178-184 */
+      int32_t first = binary ? ((int32_t)thr + 1) * s : ((int32_t)thr + 1);
+      ref_out[q] = w16((int32_t)ref_out[q] + first);
+      val_last[q] = w16(first);
+      time_last[q] = (int16_t)(uint16_t)time_now;
+      continue;
+    }
+    double time_diff, v;
+    if (!binary) {                                    /* dec:136-137 */
+      time_diff = (double)time_now - ((double)time_last[q] - ((double)nb - (double)val_last[q] * bin_width));
+      v = floor((double)nb - py_mod(time_diff, (double)per) / bin_width);
+    } else {                                          /* dec:186-190 */
+      double lg = log2((double)val_last[q]);          /* nan for negatives, -inf for 0 */
+      time_diff = (double)time_now - ((double)time_last[q] - 2.0 * (((double)nb - lg * bin_width) + 1.0));
+      v = pow(2.0, floor((double)nb - py_mod(time_diff, (double)per) / bin_width));
+    }
+    int16_t val_now;
+    int rc = f64_to_i16(v, &val_now);
+    if (rc) return rc;
+    int32_t upd = (int32_t)thr * s * (int32_t)val_now;  /* C int arithmetic, stored to int16 */
+    ref_out[q] = w16((int32_t)ref_out[q] + upd);      /* dec:141 / dec:192 */
+    val_last[q] = w16(upd);
+    time_last[q] = (int16_t)(uint16_t)time_now;
+  }
+  return 0;
+}

@@ -18,7 +18,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "dvs_oracle.c")
 _LIB = os.path.join(_HERE, "libdvs_oracle.so")
 
-ERRORS = {1: IndexError, 2: MemoryError, 3: ZeroDivisionError, 4: IndexError}
+ERRORS = {1: IndexError, 2: MemoryError, 3: ZeroDivisionError, 4: IndexError, 5: OverflowError,
+          6: ValueError}
 UP, DOWN, MERGED, RECTIFIED = 0, 1, 2, 3
 ENC_RATE, ENC_TIME, ENC_TIME_BIN, ENC_TIME_BIN_THR = 0, 1, 2, 3
 
@@ -262,6 +263,88 @@ class Oracle:
         p = self._enc_params(ENC_TIME_BIN_THR, min_threshold, num_bins, flag_shift, data_shift,
                              data_mask, log2_table, False)
         return self._encode(p, pos_spikes, neg_spikes)
+
+
+# -- numba_nvs.py float variants (in place, like the reference) -------------------
+NVS_0, NVS_LEAKY, NVS_LEAKY_ADAPTIVE, NVS_NOISY_LEAKY_ADAPTIVE = 0, 1, 2, 3
+
+
+def _f32(*arrs):
+    for a in arrs:
+        assert a.dtype == np.float32 and a.flags.c_contiguous
+
+
+def nvs_step(mode, frame, reference, thresholds, spikes, reference_leak=1.0, threshold_base=0.0,
+             threshold_mult_incr=0.0, threshold_leak=1.0, leak_mask=None):
+    """nvs_0 / nvs_leaky / nvs_leaky_adaptive / nvs_noisy_leaky_adaptive (numba_nvs.py:23-90); returns
+    the activity plane (uint8) that thresholded_difference (numba_nvs.py:6-20) returns."""
+    _f32(frame, reference, thresholds, spikes)
+    active = np.zeros(frame.shape, np.uint8)
+    if leak_mask is not None:
+        leak_mask = np.ascontiguousarray(leak_mask, dtype=np.uint8)
+    lib().orc_nvs_f32(C.c_int(mode), _p(frame), _p(reference), _p(thresholds), _p(spikes), _p(active),
+                      _p(leak_mask) if leak_mask is not None else None, C.c_double(reference_leak),
+                      C.c_double(threshold_base), C.c_double(threshold_mult_incr),
+                      C.c_double(threshold_leak), C.c_long(frame.size))
+    return active
+
+
+def nvs_bi_step(frame, reference, thresholds, spikes, reference_leak, threshold_base, threshold_mult_incr,
+                threshold_leak, reference_off, thresholds_off, target_off, leak_mask=None,
+                leak_mask_off=None, spikes_off=None):
+    """nvs_bi_noisy_leaky_adaptive (numba_nvs.py:93-147) with the two random draws injected."""
+    _f32(frame, reference, thresholds, spikes, reference_off, thresholds_off)
+    masks = [None if m is None else np.ascontiguousarray(m, dtype=np.uint8) for m in (leak_mask, leak_mask_off)]
+    lib().orc_nvs_bi_f32(_p(frame), _p(reference), _p(thresholds), _p(spikes), _p(reference_off),
+                         _p(thresholds_off), _p(spikes_off) if spikes_off is not None else None,
+                         _p(masks[0]) if masks[0] is not None else None,
+                         _p(masks[1]) if masks[1] is not None else None, C.c_double(reference_leak),
+                         C.c_double(threshold_base), C.c_double(threshold_mult_incr),
+                         C.c_double(threshold_leak), C.c_double(target_off), C.c_long(frame.size))
+
+
+# -- SURVEY 8(f) rank 3: decode_spikes.pyx ---------------------------------------------------------------
+def key_to_spike(key, flag_shift, data_shift, data_mask):
+    """decode_spikes.pyx:46-67."""
+    row = (key >> data_shift) & data_mask
+    col = key & data_mask
+    return row, col, (1 if ((key >> flag_shift) & 1) == 0 else -1)
+
+
+def update_ref_spike_list_rate(ref, spikes, threshold, history_weight, flag_shift, data_shift, data_mask):
+    """decode_spikes.pyx:71-94; returns a new reference plane."""
+    ref = _i16(ref)
+    spikes = _i16(spikes)
+    out = np.empty_like(ref)
+    _check(lib().orc_decode_rate(_p(ref), _p(out), C.c_int(ref.shape[0]), C.c_int(ref.shape[1]), _p(spikes),
+                                 C.c_long(spikes.size), C.c_int(threshold), C.c_double(history_weight),
+                                 C.c_int(flag_shift), C.c_int(data_shift), C.c_int(data_mask)))
+    return out
+
+
+def _decode_time(binary, ref, time_last, val_last, spikes, num_bins, bin_width, time_period, time_now,
+                 threshold, history_weight, flag_shift, data_shift, data_mask):
+    ref = _i16(ref)
+    spikes = _i16(spikes)
+    assert time_last.dtype == np.int16 and val_last.dtype == np.int16
+    assert time_last.flags.c_contiguous and val_last.flags.c_contiguous
+    out = np.empty_like(ref)
+    _check(lib().orc_decode_time(C.c_int(binary), _p(ref), _p(out), _p(time_last), _p(val_last),
+                                 C.c_int(ref.shape[0]), C.c_int(ref.shape[1]), _p(spikes), C.c_long(spikes.size),
+                                 C.c_int(num_bins), C.c_double(bin_width), C.c_int(time_period),
+                                 C.c_uint32(time_now), C.c_int(threshold), C.c_double(history_weight),
+                                 C.c_int(flag_shift), C.c_int(data_shift), C.c_int(data_mask)))
+    return out, time_last, val_last
+
+
+def update_ref_spike_list_time(*args):
+    """decode_spikes.pyx:98-145; mutates and returns time_last / val_last like the reference."""
+    return _decode_time(0, *args)
+
+
+def update_ref_spike_list_time_bin(*args):
+    """decode_spikes.pyx:149-197."""
+    return _decode_time(1, *args)
 
 
 class Pipeline:

@@ -1,7 +1,7 @@
 """ctypes binding of ``libpydvs_b200.so`` (``include/pydvs_b200.h``).
 
 There is no CPU path and no fallback: if the shared library has not been built, importing this module
-raises.  Build it with ``python -m pydvs_b200.build`` (or ``__graft_entry__.build()``).
+raises.  Build it with ``python pydvs_b200/build.py`` (or ``__graft_entry__.build()``).
 """
 import ctypes as C
 import os
@@ -48,6 +48,26 @@ class StepParams(C.Structure):
                 ("redo", C.c_void_p)]
 
 
+class NvsParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("reserved0", C.c_int32), ("n_px", C.c_int64),
+                ("frame", C.c_void_p), ("ref", C.c_void_p), ("thr", C.c_void_p), ("spikes", C.c_void_p),
+                ("active", C.c_void_p), ("leak_mask", C.c_void_p), ("ref_off", C.c_void_p),
+                ("thr_off", C.c_void_p), ("spikes_off", C.c_void_p), ("leak_mask_off", C.c_void_p),
+                ("reference_leak", C.c_double), ("threshold_base", C.c_double),
+                ("threshold_mult_incr", C.c_double), ("threshold_leak", C.c_double),
+                ("target_off", C.c_double)]
+
+
+class KeyList(C.Structure):
+    _fields_ = [("keys", C.c_void_p), ("stream_offsets", C.c_void_p), ("n", C.c_int64),
+                ("S", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("flag_shift", C.c_int32),
+                ("data_shift", C.c_int32), ("data_mask", C.c_int32)]
+
+
+NVS_0, NVS_LEAKY, NVS_LEAKY_ADAPTIVE, NVS_NOISY_LEAKY_ADAPTIVE, NVS_BI_NOISY_LEAKY_ADAPTIVE = 0, 1, 2, 3, 4
+DECODE_KEY_NEGATIVE, DECODE_INDEX, DECODE_VALUE_NAN, DECODE_VALUE_RANGE = 0, 1, 2, 3
+DECODE_NO_ERROR = 0x7f7f7f7f
+
 _P, _I32, _I64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 
 _SIGNATURES = {
@@ -73,6 +93,11 @@ _SIGNATURES = {
     "dvs_gather_split": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _I64, _P, _I64, _P]),
     "dvs_keys_from_events": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P]),
     "dvs_move_mask_i16": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _P, _P, _I32, _I32, _I32, _P]),
+    "dvs_nvs_step_f32": (C.c_int, [C.POINTER(NvsParams), _P]),
+    "dvs_decay_i16": (C.c_int, [_P, _P, _D, _I64, _P]),
+    "dvs_decode_rate_i16": (C.c_int, [C.POINTER(KeyList), _P, _I32, _P, _P]),
+    "dvs_decode_time_round_i16": (C.c_int, [C.POINTER(KeyList), _I32, _P, _P, _P, _P, _I32, _D, _I32,
+                                            C.c_uint32, _I32, _P, _P, _P, _P, _P]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
@@ -86,10 +111,14 @@ def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             "pydvs_b200: %s is missing. This package has no CPU fallback; build the CUDA library with "
-            "`python -m pydvs_b200.build` (needs nvcc)." % LIB_PATH)
+            "`python pydvs_b200/build.py` (needs nvcc)." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
-        fn = getattr(lib, name)  # AttributeError if the .so does not export what the header declares
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:  # the .so does not export what the header declares
+            raise ImportError("pydvs_b200: %s does not export %s (stale build): run `python pydvs_b200/build.py`"
+                              % (LIB_PATH, name))
         fn.restype, fn.argtypes = res, args
     if lib.dvs_abi_version() != ABI_VERSION:
         raise ImportError("pydvs_b200: ABI version mismatch, rebuild the library")

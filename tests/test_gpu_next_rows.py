@@ -1,0 +1,217 @@
+"""GPU parity of the rows next to the hot path through the C-ABI:
+``pydvs_b200.decode_spikes`` (decode_spikes.pyx) and ``pydvs_b200.numba_nvs`` (numba_nvs.py) against the
+CPU oracle and the golden vectors generated from the reference.  Integer planes and float32 planes must
+both be bit-exact (the float variants reproduce numba's evaluation precision exactly)."""
+import numpy as np
+import pytest
+import torch
+
+from test_oracle_next_rows import G, NVS_CASES, feq, nvs_kwargs, replay_time_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ---- decoder ---------------------------------------------------------------------------------------
+def _keys(rng, n, H, W, fs, ds):
+    return ((rng.integers(0, 2, n) << fs) | (rng.integers(0, H, n) << ds) | rng.integers(0, W, n)).astype(np.int16)
+
+
+@pytest.mark.parametrize("i", range(int(G["dec_rate_n"][0])))
+def test_decode_rate_golden(i):
+    import pydvs_b200.decode_spikes as dec
+    thr, fs, ds, mask = (int(v) for v in G["dec_rate%d_par" % i])
+    hw = float(G["dec_rate%d_hw" % i][0])
+    out = dec.update_ref_spike_list_rate(G["dec_rate%d_ref" % i].copy(), G["dec_rate%d_keys" % i], thr, hw, fs, ds, mask)
+    assert isinstance(out, np.ndarray) and np.array_equal(out, G["dec_rate%d_out" % i])
+    out = dec.update_ref_spike_list_rate(_cu(G["dec_rate%d_ref" % i]), _cu(G["dec_rate%d_keys" % i]), thr, hw, fs, ds, mask)
+    assert out.is_cuda and np.array_equal(out.cpu().numpy(), G["dec_rate%d_out" % i])
+
+
+@pytest.mark.parametrize("i", range(int(G["dec_time_n"][0])))
+@pytest.mark.parametrize("device_tensors", [False, True])
+def test_decode_time_golden(i, device_tensors):
+    import pydvs_b200.decode_spikes as dec
+    if device_tensors:
+        replay_time_case(i, dec.update_ref_spike_list_time, dec.update_ref_spike_list_time_bin, _cu,
+                         lambda t: t.cpu().numpy())
+    else:
+        replay_time_case(i, dec.update_ref_spike_list_time, dec.update_ref_spike_list_time_bin)
+
+
+def test_decoders_random_vs_oracle():
+    import pydvs_b200.decode_spikes as dec
+    from oracle import oracle as orc
+    rng = np.random.default_rng(17)
+    for trial in range(40):
+        H, W, fs, ds, mask = [(16, 16, 8, 4, 15), (64, 128, 14, 7, 127), (8, 8, 6, 3, 7)][trial % 3]
+        ref = rng.integers(-50, 300, (H, W)).astype(np.int16)
+        k = _keys(rng, int(rng.integers(0, 400)), H, W, fs, ds)   # duplicates accumulate
+        thr, hw = int(rng.integers(1, 40)), float(rng.choice([1.0, 0.99, 0.5, 0.29]))
+        assert np.array_equal(dec.update_ref_spike_list_rate(ref.copy(), k, thr, hw, fs, ds, mask),
+                              orc.update_ref_spike_list_rate(ref.copy(), k, thr, hw, fs, ds, mask))
+    for binary in (0, 1):
+        f_gpu = dec.update_ref_spike_list_time_bin if binary else dec.update_ref_spike_list_time
+        f_orc = orc.update_ref_spike_list_time_bin if binary else orc.update_ref_spike_list_time
+        for trial in range(30):
+            a = [rng.integers(0, 256, (8, 8)).astype(np.int16), np.zeros((8, 8), np.int16), np.full((8, 8), -1, np.int16)]
+            b = [x.copy() for x in a]
+            nb, bw, per = int(rng.integers(2, 9)), float(rng.choice([1.0, 0.5, 2.0, 1.5])), int(rng.integers(1, 20))
+            thr, hw, t = int(rng.integers(1, 20)), float(rng.choice([1.0, 0.99])), int(rng.integers(0, 70000))
+            for _step in range(5):
+                k = _keys(rng, int(rng.integers(0, 40)), 8, 8, 6, 3)   # pixels repeat: several rounds on the GPU
+                t += int(rng.integers(1, 40))
+                ea = eb = None
+                try:
+                    a = list(f_gpu(a[0], a[1], a[2], k, nb, bw, per, t, thr, hw, 6, 3, 7))
+                except (ValueError, OverflowError) as e:
+                    ea = type(e)
+                try:
+                    b = list(f_orc(b[0], b[1], b[2], k, nb, bw, per, t, thr, hw, 6, 3, 7))
+                except (ValueError, OverflowError) as e:
+                    eb = type(e)
+                assert ea is eb, (binary, trial, ea, eb)
+                if ea is not None:
+                    break
+                assert all(np.array_equal(x, y) for x, y in zip(a, b)), (binary, trial)
+
+
+def test_decoder_errors():
+    import pydvs_b200.decode_spikes as dec
+    ref = np.zeros((8, 8), np.int16)
+    with pytest.raises(OverflowError):
+        dec.update_ref_spike_list_rate(ref, np.array([3, -5], np.int16), 12, 1.0, 6, 3, 7)
+    with pytest.raises(IndexError):
+        dec.update_ref_spike_list_rate(ref, np.array([(9 << 4) | 1], np.int16), 12, 1.0, 8, 4, 15)
+    with pytest.raises(ValueError):
+        dec.update_ref_spike_list_rate(ref.astype(np.int32), np.array([3], np.int16), 12, 1.0, 6, 3, 7)
+    with pytest.raises(OverflowError):
+        dec.update_ref_spike_list_rate(ref, np.array([3], np.int16), 70000, 1.0, 6, 3, 7)
+    assert dec.key_to_spike(0x123, 8, 4, 15) == (2, 3, -1)
+    with pytest.raises(OverflowError):
+        dec.key_to_spike(-1, 8, 4, 15)
+
+
+def test_encode_decode_round_trip_many_streams():
+    """Size-independent property: with the uncoded rate encoder (k = min(max_time_ms - 1, v) events of weight
+    `threshold` per pixel) and history_weight 1, the receiver's plane moves by exactly the opposite of the
+    sender's reference (the decoder maps flag 1 to -1) as long as v < max_time_ms and nothing
+    clips: ref_sender + ref_receiver == 2 * ref0."""
+    import pydvs_b200.decode_spikes as dec
+    from pydvs_b200 import DVSConfig, DVSStreams
+    S, H, W, T, mt = 96, 128, 128, 12, 16
+    cfg = DVSConfig(width=W, height=H, streams=S, output_type="RATE", threshold=T, max_time_ms=mt, uncoded=True, ref0=128)
+    dvs = DVSStreams(cfg, event_capacity=S * H * W * 10)
+    receiver = torch.full((S, H, W), 128, dtype=torch.int16, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(4):
+        # frames within 128 +- 40: references stay well inside [0, 255] and v = |d| // 12 <= 8 < max_time_ms - 1
+        frames = (128 + torch.randint(-40, 41, (S, H, W), device="cuda", generator=g)).to(torch.int16)
+        res = dvs.step(frames)
+        keys = res.keys(14, 7, 127)                     # uncoded layout, all streams, stream-major
+        assert keys.numel() == res.total_events() > 0
+        # per-stream offsets: every (2 * n_slots)-th entry of the CSR over (stream, slot, polarity)
+        offs = res.seg_offsets[::2 * dvs.n_slots].contiguous()
+        assert offs.numel() == S + 1
+        receiver = dec.decode_rate_batch(receiver, keys, offs, T, 1.0, 14, 7, 127)
+    assert torch.equal(dvs.ref.to(torch.int32) + receiver.to(torch.int32),
+                       torch.full((S, H, W), 256, dtype=torch.int32, device="cuda"))
+
+
+# ---- numba float variants ------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,mode,mask", NVS_CASES)
+@pytest.mark.parametrize("device_tensors", [False, True])
+def test_nvs_golden(tag, mode, mask, device_tensors):
+    import pydvs_b200.numba_nvs as nvs
+    kw, _ = nvs_kwargs()
+    conv = _cu if device_tensors else (lambda a: a.copy())
+    r, t = conv(G["nvs_ref0"]), conv(G["nvs_thr0"])
+    s = conv(np.zeros_like(G["nvs_ref0"]))
+    m = None if mask is None else np.full(G["nvs_ref0"].shape, mask, np.uint8)
+    a = (kw["reference_leak"], kw["threshold_base"], kw["threshold_mult_incr"], kw["threshold_leak"])
+    for f in G["nvs_frames"]:
+        f = conv(f)
+        if tag == "nvs_0":
+            nvs.nvs_0(f, r, t, s)
+        elif tag == "nvs_leaky":
+            nvs.nvs_leaky(f, r, t, s, a[0])
+        elif tag == "nvs_leaky_adaptive":
+            nvs.nvs_leaky_adaptive(f, r, t, s, *a)
+        else:
+            nvs.nvs_noisy_leaky_adaptive(f, r, t, s, *a, 0.5, leak_mask=m)
+    host = (lambda x: x.cpu().numpy()) if device_tensors else (lambda x: x)
+    assert feq(host(r), G[tag + "_ref"]) and feq(host(t), G[tag + "_thr"]) and feq(host(s), G[tag + "_spikes"])
+
+
+@pytest.mark.parametrize("tag,mask", [("nvs_bi_noisy_leaky_adaptive_all", 1), ("nvs_bi_noisy_leaky_adaptive_none", 0)])
+def test_nvs_two_cell_golden(tag, mask):
+    import pydvs_b200.numba_nvs as nvs
+    kw, target = nvs_kwargs()
+    r, t = G["nvs_ref0"].copy(), G["nvs_thr0"].copy()
+    ro, to = r[::-1].copy(), t[::-1].copy()
+    s = np.zeros_like(r)
+    m = np.full(r.shape, mask, np.uint8)
+    for f in G["nvs_frames"]:
+        nvs.nvs_bi_noisy_leaky_adaptive(f.copy(), r, t, s, kw["reference_leak"], kw["threshold_base"],
+                                        kw["threshold_mult_incr"], kw["threshold_leak"], 0.5, ro, to, target,
+                                        leak_mask=m, leak_mask_off=m)
+    for got, name in ((r, "_ref"), (t, "_thr"), (s, "_spikes"), (ro, "_ref_off"), (to, "_thr_off")):
+        assert feq(got, G[tag + name]), name
+
+
+def test_nvs_thresholded_difference():
+    import pydvs_b200.numba_nvs as nvs
+    r, t = G["nvs_ref0"].copy(), G["nvs_thr0"].copy()
+    s = np.zeros_like(r)
+    active = nvs.thresholded_difference(G["nvs_frames"][0].copy(), r, t, s)
+    assert active.dtype == np.uint8 and np.array_equal(active, G["nvs_td_active"])
+    assert np.array_equal(r, G["nvs_ref0"])  # the reference plane is left alone
+
+
+def test_nvs_random_batched_vs_oracle():
+    """[S, H, W] batches with random per-pixel leak masks, odd sizes (scalar tail) and unaligned views."""
+    import pydvs_b200.numba_nvs as nvs
+    from oracle import oracle as orc
+    rng = np.random.default_rng(23)
+    kw = dict(reference_leak=0.9, threshold_base=7.5, threshold_mult_incr=0.77, threshold_leak=0.81)
+    a = (0.9, 7.5, 0.77, 0.81)
+    for shape in ((3, 33, 47), (2, 64, 128), (1, 5, 7)):
+        f = rng.uniform(0, 255, shape).astype(np.float32)
+        planes = [rng.uniform(0, 255, shape).astype(np.float32), rng.uniform(-3, 40, shape).astype(np.float32),
+                  np.zeros(shape, np.float32), rng.uniform(0, 255, shape).astype(np.float32),
+                  rng.uniform(1, 40, shape).astype(np.float32)]
+        m1, m2 = rng.integers(0, 2, shape).astype(np.uint8), rng.integers(0, 2, shape).astype(np.uint8)
+        exp = [p.copy() for p in planes]
+        got = [_cu(p) for p in planes]
+        fc = _cu(f)
+        for _it in range(3):
+            orc.nvs_bi_step(f, exp[0], exp[1], exp[2], *a, exp[3], exp[4], 99.5, leak_mask=m1, leak_mask_off=m2)
+            nvs.nvs_bi_noisy_leaky_adaptive(fc, got[0], got[1], got[2], *a, 0.5, got[3], got[4], 99.5, leak_mask=m1,
+                                            leak_mask_off=m2)
+        assert all(feq(g.cpu().numpy(), e) for g, e in zip(got, exp)), shape
+        exp = [p.copy() for p in planes[:3]]
+        got = [_cu(p) for p in planes[:3]]
+        for _it in range(3):
+            orc.nvs_step(orc.NVS_NOISY_LEAKY_ADAPTIVE, f, exp[0], exp[1], exp[2], leak_mask=m1, **kw)
+            nvs.nvs_noisy_leaky_adaptive(fc, got[0], got[1], got[2], *a, 0.5, leak_mask=_cu(m1))
+        assert all(feq(g.cpu().numpy(), e) for g, e in zip(got, exp)), shape
+
+
+def test_nvs_device_generated_mask_is_seeded_and_has_the_right_rate():
+    import pydvs_b200.numba_nvs as nvs
+    shape = (4, 128, 256)
+    outs = []
+    for _rep in range(2):
+        g = torch.Generator(device="cuda").manual_seed(77)
+        f = torch.full(shape, 50.0, device="cuda")
+        r = torch.full(shape, 100.0, device="cuda")
+        t = torch.full(shape, 1000.0, device="cuda")   # never spikes: the reference only leaks
+        s = torch.zeros(shape, device="cuda")
+        nvs.nvs_noisy_leaky_adaptive(f, r, t, s, 0.5, 1000.0, 0.0, 1.0, 0.25, generator=g)
+        outs.append(r.clone())
+    assert torch.equal(outs[0], outs[1])
+    leaked = (outs[0] == 50.0).float().mean().item()
+    assert abs(leaked - 0.25) < 0.01 and bool(((outs[0] == 50.0) | (outs[0] == 100.0)).all())
