@@ -273,6 +273,14 @@ typedef struct dvs_nvs_params {
 } dvs_nvs_params;
 int dvs_nvs_step_f32(const dvs_nvs_params *p, void *stream);
 
+/* Batched frame animators (the step before the path): stream s shows images[img_index[s]] at its own
+ * frame_number[s].  DVS_ANIM_TRAVERSE = traverse_image gs:1128-1152 (`speed` pixels per frame, vacated
+ * pixels = bg); DVS_ANIM_FADE = fade_image gs:1156-1182 (`half_frame`; float64 alpha, truncation). */
+enum { DVS_ANIM_TRAVERSE = 0, DVS_ANIM_FADE = 1 };
+int dvs_animate_i16(int32_t mode, const int16_t *images, int32_t n_images, const int32_t *img_index,
+                    const int32_t *frame_number, double speed, int32_t half_frame, int32_t bg, int16_t *out,
+                    int32_t S, int32_t H, int32_t W, void *stream);
+
 /* Receiver, pydvs/decode_spikes.pyx ("dec").  ref_out = int16(ref * history_weight), the first
  * statement of every update_ref_spike_list_* (dec:85, 121, 172). */
 int dvs_decay_i16(const int16_t *ref, int16_t *ref_out, double history_weight, int64_t n_px, void *stream);

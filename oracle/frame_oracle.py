@@ -28,3 +28,29 @@ def move_image(original, delta_x, delta_y, bg_gray):
 
 def mask_image(original, mask):
     return np.int16(original * mask)
+
+
+def traverse_image(original, frame_number, speed, bg_gray):
+    """generate_spikes.pyx:1128-1152, slice for slice."""
+    moved = bg_gray * np.ones_like(original, dtype=np.int16)
+    width = original.shape[1]
+    n = int(np.int16(int(np.int16(frame_number) * float(speed))))
+    if n == 0:
+        n = 1
+    if n <= width:
+        moved[:, :n] = original[:, -n:]
+    elif n < 2 * width:
+        n = 2 * width - n + 1
+        moved[:, -n:] = original[:, :n]
+    return moved
+
+
+def fade_image(original, frame_number, half_frame, bg_gray):
+    """generate_spikes.pyx:1156-1182 (bg_gray is overwritten by the final assignment)."""
+    if frame_number < half_frame - 1:
+        alpha = float(frame_number) / float(half_frame)
+    elif frame_number > half_frame + 1:
+        alpha = float(int(np.int16(half_frame * 2 - frame_number))) / float(half_frame)
+    else:
+        alpha = 1.0
+    return np.int16(original * alpha)

@@ -67,6 +67,7 @@ class KeyList(C.Structure):
 NVS_0, NVS_LEAKY, NVS_LEAKY_ADAPTIVE, NVS_NOISY_LEAKY_ADAPTIVE, NVS_BI_NOISY_LEAKY_ADAPTIVE = 0, 1, 2, 3, 4
 DECODE_KEY_NEGATIVE, DECODE_INDEX, DECODE_VALUE_NAN, DECODE_VALUE_RANGE = 0, 1, 2, 3
 DECODE_NO_ERROR = 0x7f7f7f7f
+ANIM_TRAVERSE, ANIM_FADE = 0, 1
 
 _P, _I32, _I64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 
@@ -93,6 +94,7 @@ _SIGNATURES = {
     "dvs_gather_split": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _I64, _P, _I64, _P]),
     "dvs_keys_from_events": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P]),
     "dvs_move_mask_i16": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _P, _P, _I32, _I32, _I32, _P]),
+    "dvs_animate_i16": (C.c_int, [_I32, _P, _I32, _P, _P, _D, _I32, _I32, _P, _I32, _I32, _I32, _P]),
     "dvs_nvs_step_f32": (C.c_int, [C.POINTER(NvsParams), _P]),
     "dvs_decay_i16": (C.c_int, [_P, _P, _D, _I64, _P]),
     "dvs_decode_rate_i16": (C.c_int, [C.POINTER(KeyList), _P, _I32, _P, _P]),

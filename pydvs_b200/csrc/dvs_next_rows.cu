@@ -323,6 +323,48 @@ __global__ void __launch_bounds__(256) k_decode_time(KeyArgs K, int binary, uint
   time_last[q] = (int16_t)(unsigned short)time_now;
 }
 
+// ---- frame animators gs:1128-1182, batched over streams -----------------------------------------
+// mode 0: traverse_image gs:1128-1152 -- n = int16(frame_number * speed) (0 -> 1); n <= W: the last n columns of
+//         the image enter from the left (NumPy slice rules, so a negative n shifts left by |n|); W < n < 2W:
+//         with n' = 2W - n + 1 the first n' columns leave on the right; otherwise background.
+// mode 1: fade_image gs:1156-1182 -- int16(original * alpha), alpha = f / half before half - 1,
+//         (2 half - f) / half after half + 1, else 1 (float64, truncation; bg_gray is overwritten).
+__global__ void __launch_bounds__(256) k_animate(int mode, const int16_t *__restrict__ images, int n_images,
+                                                 const int32_t *__restrict__ img_index,
+                                                 const int32_t *__restrict__ frame_number, double speed, int half_frame,
+                                                 int bg, int16_t *__restrict__ out, int S, int H, int W) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long P = (long long)H * W;
+  if (g >= (long long)S * P) return;
+  const int s = (int)(g / P);
+  const int q = (int)(g - (long long)s * P);
+  const int y = q / W, x = q - y * W;
+  const int img = img_index[s];
+  const bool have = img >= 0 && img < n_images;
+  const int16_t *src = images + (long long)(have ? img : 0) * P + (long long)y * W;
+  const int fn = (int16_t)frame_number[s];
+  int v = bg;
+  if (mode == 0) {
+    int n = (int16_t)__double2int_rz(__dmul_rn((double)fn, speed));
+    if (n == 0) n = 1;
+    int sx = -1;
+    if (n <= W) {
+      if (n > 0) { if (x < n) sx = W - n + x; }
+      else if (x < W + n) sx = x - n;
+    } else if (n < 2 * W) {
+      const int m = 2 * W - n + 1;
+      if (x >= W - m) sx = x - (W - m);
+    }
+    if (sx >= 0 && have) v = src[sx];
+  } else {
+    double alpha = 1.0;
+    if (fn < half_frame - 1) alpha = __ddiv_rn((double)fn, (double)half_frame);
+    else if (fn > half_frame + 1) alpha = __ddiv_rn((double)(int16_t)(half_frame * 2 - fn), (double)half_frame);
+    v = have ? (int)(int16_t)__double2int_rz(__dmul_rn((double)src[x], alpha)) : 0;
+  }
+  out[g] = (int16_t)v;
+}
+
 cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 int launch_status(const char *what) {
   (void)what;
@@ -363,6 +405,18 @@ int dvs_nvs_step_f32(const dvs_nvs_params *p, void *stream) {
     default: k_nvs<4><<<blocks, 256, 0, st>>>(A, vec); break;
   }
   return launch_status("k_nvs");
+}
+
+int dvs_animate_i16(int32_t mode, const int16_t *images, int32_t n_images, const int32_t *img_index,
+                    const int32_t *frame_number, double speed, int32_t half_frame, int32_t bg, int16_t *out, int32_t S,
+                    int32_t H, int32_t W, void *stream) {
+  if (!images || !img_index || !frame_number || !out || n_images <= 0 || S <= 0 || H <= 0 || W <= 0 ||
+      (mode != DVS_ANIM_TRAVERSE && mode != DVS_ANIM_FADE))
+    return dvs::set_error(DVS_ERR_INVALID_ARGUMENT, "animate arguments");
+  const long long n = (long long)S * H * W;
+  k_animate<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(mode, images, n_images, img_index, frame_number, speed,
+                                                                     half_frame, bg, out, S, H, W);
+  return launch_status("k_animate");
 }
 
 int dvs_decay_i16(const int16_t *ref, int16_t *ref_out, double history_weight, int64_t n_px, void *stream) {

@@ -43,6 +43,38 @@ def move_images(images, img_index, dx, dy, bg=0, mask=None, out=None):
     return out
 
 
+def _animate(mode, images, img_index, frame_number, speed, half_frame, bg, out):
+    if images.dtype != torch.int16 or images.dim() != 3 or not images.is_cuda:
+        raise ValueError("images must be a CUDA int16 tensor [N, H, W]")
+    n, H, W = images.shape
+    dev = images.device
+    idx = torch.as_tensor(img_index, dtype=torch.int32, device=dev).contiguous()
+    fn = torch.as_tensor(frame_number, dtype=torch.int32, device=dev).contiguous()
+    S = idx.numel()
+    if fn.numel() == 1 and S > 1:
+        fn = fn.expand(S).contiguous()
+    if fn.numel() != S:
+        raise ValueError("frame_number must be a scalar or have one entry per stream")
+    if out is None:
+        out = torch.empty((S, H, W), dtype=torch.int16, device=dev)
+    images = images.contiguous()
+    check(lib.dvs_animate_i16(mode, C.c_void_p(images.data_ptr()), n, C.c_void_p(idx.data_ptr()), C.c_void_p(fn.data_ptr()),
+                              float(speed), int(half_frame), int(bg), C.c_void_p(out.data_ptr()), S, H, W, _stream()))
+    return out
+
+
+def traverse_images(images, img_index, frame_number, speed, bg=0, out=None):
+    """Batched ``traverse_image`` (``generate_spikes.pyx:1128-1152``): stream s shows images[img_index[s]] sliding in
+    from the left / out to the right at ``speed`` pixels per frame, at its own ``frame_number[s]``."""
+    return _animate(0, images, img_index, frame_number, speed, 0, bg, out)
+
+
+def fade_images(images, img_index, frame_number, half_frame, bg=0, out=None):
+    """Batched ``fade_image`` (``generate_spikes.pyx:1156-1182``): ``int16(original * alpha)`` with the triangular
+    alpha profile peaking at ``half_frame``."""
+    return _animate(1, images, img_index, frame_number, 0.0, half_frame, bg, out)
+
+
 def saccade_offsets(n_streams, n_frames, frames_per_microsaccade=1, max_dist=1, seed=0):
     """Per-frame (cx, cy) of every stream following mnist_to_spikes.py:246-258: frame 0 shows the image
     unmoved; on frames that are multiples of `frames_per_microsaccade` both offsets take a uniform step in

@@ -66,3 +66,24 @@ def calculate_time_per_pack(output_type, max_time_ms, min_threshold, max_thresho
     if output_type == OUTPUT_TIME_BIN:
         return max_time_ms // 8
     return max_time_ms // (num_bits_per_spike + 1)
+
+
+def emit_spikes(sender, lists, time_per_spike_pack_ms, label, clock=None, sleep=None):
+    """Slot-paced emission, ``external_dvs_emulator_device.py:532-545``: one ``sender.send_spikes(label, pack,
+    send_full_keys=False)`` per time slot, then sleep for the rest of ``time_per_spike_pack_ms``.  ``lists`` is
+    what ``make_spike_lists_*`` / ``StepResult.spike_lists`` return; ``clock`` / ``sleep`` default to
+    ``time.time`` / ``time.sleep`` and can be injected (tests, simulated time).  Returns the number of packs sent."""
+    import time
+    clock = clock or time.time
+    sleep = sleep or time.sleep
+    max_time_s = time_per_spike_pack_ms / 1000.
+    sent = 0
+    if lists is not None:
+        for spike_pack in lists:
+            start = clock()
+            sender.send_spikes(label, spike_pack, send_full_keys=False)
+            elapsed = clock() - start
+            if elapsed < max_time_s:
+                sleep(max_time_s - elapsed)
+            sent += 1
+    return sent

@@ -144,6 +144,18 @@ def main():
     a = nvs.thresholded_difference(frames[0].copy(), ref0.copy(), thr0.copy(), np.zeros_like(ref0))
     out["nvs_td_active"] = np.asarray(a, np.uint8)
 
+    # ---- frame animators (generate_spikes.pyx:1128-1182) ------------------------------------------
+    gs = mods[0]
+    rng = np.random.default_rng(77)
+    img = rng.integers(0, 256, (12, 20)).astype(np.int16)
+    out["anim_img"] = img
+    trav = [(fn, sp) for sp in (0.5, 1.0, 1.7, 3.3, -1.0) for fn in (0, 1, 5, 12, 13, 20, 24, 39, 41, 70)]
+    out["anim_trav_par"] = np.array(trav, np.float64)
+    out["anim_trav_out"] = np.stack([gs.traverse_image(img, int(fn), float(sp), 37) for fn, sp in trav])
+    fade = [(fn, hf) for hf in (1, 7, 15) for fn in (0, 1, 5, 6, 7, 8, 9, 14, 16, 29, 31)]
+    out["anim_fade_par"] = np.array(fade, np.int64)
+    out["anim_fade_out"] = np.stack([gs.fade_image(img, int(fn), int(hf), 37) for fn, hf in fade])
+
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_next_v1.npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays, %d bytes" % (path, len(out), os.path.getsize(path)))

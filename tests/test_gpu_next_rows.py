@@ -215,3 +215,39 @@ def test_nvs_device_generated_mask_is_seeded_and_has_the_right_rate():
     assert torch.equal(outs[0], outs[1])
     leaked = (outs[0] == 50.0).float().mean().item()
     assert abs(leaked - 0.25) < 0.01 and bool(((outs[0] == 50.0) | (outs[0] == 100.0)).all())
+
+
+# ---- batched frame animators -------------------------------------------------------------------------
+def test_traverse_and_fade_golden_batched():
+    """Every golden case is one stream of a single batched launch."""
+    from pydvs_b200 import frame_sources as fs
+    img = _cu(G["anim_img"]).unsqueeze(0)
+    for sp in np.unique(G["anim_trav_par"][:, 1]):
+        sel = G["anim_trav_par"][:, 1] == sp
+        fn = G["anim_trav_par"][sel, 0].astype(np.int32)
+        out = fs.traverse_images(img, np.zeros(len(fn), np.int32), fn, float(sp), bg=37)
+        assert np.array_equal(out.cpu().numpy(), G["anim_trav_out"][sel]), sp
+    for hf in np.unique(G["anim_fade_par"][:, 1]):
+        sel = G["anim_fade_par"][:, 1] == hf
+        fn = G["anim_fade_par"][sel, 0].astype(np.int32)
+        out = fs.fade_images(img, np.zeros(len(fn), np.int32), fn, int(hf), bg=37)
+        assert np.array_equal(out.cpu().numpy(), G["anim_fade_out"][sel]), hf
+
+
+def test_traverse_and_fade_random_vs_oracle():
+    from oracle import frame_oracle as fo
+    from pydvs_b200 import frame_sources as fs
+    rng = np.random.default_rng(9)
+    for H, W in ((28, 28), (33, 47), (64, 128)):
+        imgs = rng.integers(0, 256, (5, H, W)).astype(np.int16)
+        S = 24
+        idx = rng.integers(0, 5, S).astype(np.int32)
+        fn = rng.integers(0, 3 * W, S).astype(np.int32)
+        for sp in (0.5, 1.0, 2.6, -0.7):
+            out = fs.traverse_images(_cu(imgs), idx, fn, sp, bg=11).cpu().numpy()
+            for s in range(S):
+                assert np.array_equal(out[s], fo.traverse_image(imgs[idx[s]], int(fn[s]), sp, 11)), (H, W, sp, s)
+        for hf in (3, 20, 45):
+            out = fs.fade_images(_cu(imgs), idx, fn, hf, bg=11).cpu().numpy()
+            for s in range(S):
+                assert np.array_equal(out[s], fo.fade_image(imgs[idx[s]], int(fn[s]), hf, 11)), (H, W, hf, s)

@@ -174,3 +174,14 @@ def test_nvs_live_against_numba():
                 nvs.nvs_leaky_adaptive(f, a[0], a[1], a[2], 0.9, 7.5, 0.77, 0.81)
                 orc.nvs_step(orc.NVS_LEAKY_ADAPTIVE, f, b[0], b[1], b[2], **kw)
             assert all(feq(x, y) for x, y in zip(a, b))
+
+
+# ---- frame animators -------------------------------------------------------------------------------
+def test_traverse_and_fade_golden():
+    from oracle import frame_oracle as fo
+    img = G["anim_img"]
+    for (fn, sp), want in zip(G["anim_trav_par"], G["anim_trav_out"]):
+        assert np.array_equal(fo.traverse_image(img, int(fn), float(sp), 37), want), (fn, sp)
+    for (fn, hf), want in zip(G["anim_fade_par"], G["anim_fade_out"]):
+        got = fo.fade_image(img, int(fn), int(hf), 37)
+        assert got.dtype == np.int16 and np.array_equal(got, want), (fn, hf)

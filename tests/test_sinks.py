@@ -46,3 +46,28 @@ def test_time_per_pack_rule():
     assert calculate_time_per_pack("TIME", 16, 6, 168, 4) == 16 // min(16, 168 // 6 + 1)
     assert calculate_time_per_pack("TIME_BIN", 16, 6, 168, 4) == 2
     assert calculate_time_per_pack("TIME_BIN_THR", 16, 6, 168, 4) == 3
+
+
+def test_emit_spikes_is_paced_per_slot():
+    from pydvs_b200.sinks import emit_spikes
+
+    class Sender:
+        def __init__(self):
+            self.calls = []
+
+        def send_spikes(self, label, pack, send_full_keys=True):
+            self.calls.append((label, list(pack), send_full_keys))
+            now[0] += cost.pop(0)
+
+    now, slept = [100.0], []
+    cost = [0.0002, 0.0030, 0.0005]          # the second pack takes longer than its 2 ms budget
+
+    def sleep(dt):
+        slept.append(round(dt, 6))
+        now[0] += dt
+
+    s = Sender()
+    n = emit_spikes(s, [[1, 2], [], [7]], 2, "retina", clock=lambda: now[0], sleep=sleep)
+    assert n == 3 and s.calls == [("retina", [1, 2], False), ("retina", [], False), ("retina", [7], False)]
+    assert slept == [0.0018, 0.0015]
+    assert emit_spikes(s, None, 2, "retina", clock=lambda: now[0], sleep=sleep) == 0
