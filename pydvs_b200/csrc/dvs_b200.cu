@@ -111,18 +111,31 @@ __global__ void __launch_bounds__(256) k_scan_tiles(int n_rows, int tps, const u
   if (lane == 0) totals[gw] = carry;
 }
 
-// single CTA: CSR row pointers over (stream, slot, polarity) from the stream totals
+// single CTA: CSR row pointers over (stream, slot, polarity) from the stream totals.  A thread owns whole
+// streams (a contiguous run of them), so neighbouring threads read neighbouring rows of `totals` and no
+// index arithmetic beyond two nested loops is needed.
 __global__ void __launch_bounds__(1024) k_scan_segments(int S, int n_slots, const uint32_t *__restrict__ totals,
                                                         long long *__restrict__ seg_offsets) {
   __shared__ long long wsum[32];
   __shared__ long long carry_sm;
   const int C = 2 + 2 * n_slots, per = 2 * n_slots;
-  const long long n = (long long)S * per;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long chunk = (n + blockDim.x - 1) / blockDim.x;
-  const long long lo = min(n, (long long)tid * chunk), hi = min(n, lo + chunk);
+  const int chunk = (S + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int lo = min(S, tid * chunk), hi = min(S, lo + chunk);
+  // the thread's rows are one contiguous run of words: walk it flat and unrolled so that eight loads are in
+  // flight at a time (a single CTA is latency-bound otherwise); the first two words of a row are not slots
+  const uint32_t *base = totals + (long long)lo * C;
+  const int n_words = (hi - lo) * C;
   long long sum = 0;
-  for (long long i = lo; i < hi; ++i) sum += totals[(i / per) * C + 2 + (i % per)];
+  {
+    int c = 0;
+#pragma unroll 8
+    for (int i = 0; i < n_words; ++i) {
+      const uint32_t v = base[i];
+      if (c >= 2) sum += v;
+      if (++c == C) c = 0;
+    }
+  }
   long long x = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -143,11 +156,88 @@ __global__ void __launch_bounds__(1024) k_scan_segments(int S, int n_slots, cons
   }
   __syncthreads();
   long long run = wsum[warp] + x - sum;
-  for (long long i = lo; i < hi; ++i) {
-    seg_offsets[i] = run;
-    run += totals[(i / per) * C + 2 + (i % per)];
+  {
+    long long *out = seg_offsets + (long long)lo * per;
+    int c = 0;
+#pragma unroll 8
+    for (int i = 0; i < n_words; ++i) {
+      const uint32_t v = base[i];
+      if (c >= 2) {
+        *out++ = run;
+        run += v;
+      }
+      if (++c == C) c = 0;
+    }
   }
-  if (tid == 0) seg_offsets[n] = carry_sm;
+  if (tid == 0) seg_offsets[(long long)S * per] = carry_sm;
+}
+
+// Many streams (S * 2 * n_slots > 8192 segments): a single CTA would have to pull megabytes through one SM.
+// Three small launches instead, using seg_offsets itself as scratch: (1) one thread per stream sums its row
+// into seg_offsets[s * per]; (2) one CTA scans those S values in place (exclusive); (3) one thread per stream
+// expands its base into the stream's 2 * n_slots row pointers.
+__global__ void __launch_bounds__(128) k_seg_stream_sums(int S, int n_slots, const uint32_t *__restrict__ totals,
+                                                         long long *__restrict__ seg_offsets) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int C = 2 + 2 * n_slots, per = 2 * n_slots;
+  const uint32_t *row = totals + (long long)s * C + 2;
+  long long sum = 0;
+#pragma unroll 4
+  for (int j = 0; j < per; ++j) sum += row[j];
+  seg_offsets[(long long)s * per] = sum;
+}
+
+__global__ void __launch_bounds__(1024) k_seg_scan_streams(int S, int per, long long *__restrict__ seg_offsets) {
+  __shared__ long long wsum[32];
+  __shared__ long long carry_sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunk = (S + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int lo = min(S, tid * chunk), hi = min(S, lo + chunk);
+  long long sum = 0;
+#pragma unroll 4
+  for (int s = lo; s < hi; ++s) sum += seg_offsets[(long long)s * per];
+  long long x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long y = __shfl_up_sync(kFull, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    long long w = wsum[lane], wx = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long y = __shfl_up_sync(kFull, wx, o);
+      if (lane >= o) wx += y;
+    }
+    wsum[lane] = wx - w;
+    if (lane == 31) carry_sm = wx;
+  }
+  __syncthreads();
+  long long run = wsum[warp] + x - sum;
+  for (int s = lo; s < hi; ++s) {
+    const long long v = seg_offsets[(long long)s * per];
+    seg_offsets[(long long)s * per] = run;
+    run += v;
+  }
+  if (tid == 0) seg_offsets[(long long)S * per] = carry_sm;
+}
+
+__global__ void __launch_bounds__(128) k_seg_fill(int S, int n_slots, const uint32_t *__restrict__ totals,
+                                                  long long *__restrict__ seg_offsets) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int C = 2 + 2 * n_slots, per = 2 * n_slots;
+  const uint32_t *row = totals + (long long)s * C + 2;
+  long long *out = seg_offsets + (long long)s * per;
+  long long run = out[0];
+#pragma unroll 4
+  for (int j = 0; j < per; ++j) {
+    out[j] = run;
+    run += row[j];
+  }
 }
 
 // ================================================================================================
@@ -785,8 +875,15 @@ int dvs_scan_tiles(int32_t S, int32_t tiles_per_stream, int32_t n_slots, const u
       if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
       return DVS_OK;
     }
-    k_scan_segments<<<1, 1024, 0, as_stream(stream)>>>(S, n_slots, stream_totals,
-                                                       reinterpret_cast<long long *>(seg_offsets));
+    long long *seg = reinterpret_cast<long long *>(seg_offsets);
+    if ((long long)S * 2 * n_slots <= 8192) {
+      k_scan_segments<<<1, 1024, 0, as_stream(stream)>>>(S, n_slots, stream_totals, seg);
+    } else {
+      const unsigned blocks = (unsigned)((S + 127) / 128);
+      k_seg_stream_sums<<<blocks, 128, 0, as_stream(stream)>>>(S, n_slots, stream_totals, seg);
+      k_seg_scan_streams<<<1, 1024, 0, as_stream(stream)>>>(S, 2 * n_slots, seg);
+      k_seg_fill<<<blocks, 128, 0, as_stream(stream)>>>(S, n_slots, stream_totals, seg);
+    }
     rc = check_launch("k_scan_segments");
   }
   return rc;

@@ -165,6 +165,12 @@ def test_degenerate_slot_counts():
     _run_case(1, 2, 8, inh=2, frames=3, debug=False)
 
 
+def test_many_streams_use_the_multi_block_segment_scan():
+    # S * 2 * n_slots > 8192 segments: stream sums / scan / fill run as three launches
+    _run_case(1100, 8, 16, frames=2, debug=False, threshold=3)
+    _run_case(700, 8, 16, output_type="TIME_BIN_THR", adaptive=True, num_bins=6, hw=0.99, frames=2, debug=False)
+
+
 def test_wide_tile_variant():
     # W * inh_k > 8192 pixels per tile -> the 1024-thread generic variant
     _run_case(1, 8, 2064, inh=4, frames=3)
