@@ -336,7 +336,8 @@ def run_ours(args, wl, rank, local_rank, world):
     # frame 0 is dense (ref0 = 128 vs background 64): ~2 events per pixel, a quarter of that with 2x2 inhibition
     per_px_events = (1.0 if wl["inh"] > 1 else 3.0) if args.pattern == "bar" else 3.0
     depth = 1 if args.graph else args.pipeline_depth
-    dvs = DVSStreams(cfg, device=device, event_capacity=int(max(1 << 20, S * P * per_px_events)), pipeline_depth=depth)
+    dvs = DVSStreams(cfg, device=device, event_capacity=int(max(1 << 20, S * P * per_px_events)), pipeline_depth=depth,
+                     split_lists=False)  # AER events are the output; split_spikes lists are not requested
     ring = make_ring(wl, S, args.ring, args.pattern, args.frame_dtype, device, stream_base)
     torch.cuda.synchronize()
 
@@ -423,7 +424,7 @@ def run_ours(args, wl, rank, local_rank, world):
                 legs[kind] = run_e2e(args, dvs, ring, S, P, device, world, barrier, kind)
             else:  # same streams, other input dtype: its own state object, frames converted once (untimed)
                 cfg2 = DVSConfig(**{**cfg.__dict__, "frame_dtype": kind})
-                dvs2 = DVSStreams(cfg2, device=device, event_capacity=dvs.event_capacity)  # e2e legs run in line
+                dvs2 = DVSStreams(cfg2, device=device, event_capacity=dvs.event_capacity, split_lists=False)  # e2e legs run in line
                 ring2 = [f.to(torch.uint8 if kind == "uint8" else torch.int16) for f in ring]
                 for i in range(max(args.settle, 0) + 3):
                     dvs2.step(ring2[i % len(ring2)])

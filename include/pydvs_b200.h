@@ -132,7 +132,8 @@ typedef struct dvs_step_params {
   int32_t inh_k;            /* local_inhibition area width; <= 1: off                         */
   int32_t polarity;         /* DVS_POL_*                                                      */
   int32_t force_generic;    /* 1: never take the specialised fast kernel (testing / profiling) */
-  int32_t reserved0;
+  int32_t drop_silent;      /* 1: records that emit no event (coded rate, k == 0) may be left out of the
+                             * tile lists: identical events, but the lists no longer are split_spikes' output */
   double history_weight;
   dvs_enc_params enc;
   const void *curr;         /* [S][H][W] frames, int16 or uint8                               */

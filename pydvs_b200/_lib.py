@@ -40,7 +40,7 @@ class StepParams(C.Structure):
                 ("update_mode", C.c_int32), ("uncoded", C.c_int32), ("threshold", C.c_int32),
                 ("min_thr", C.c_int32), ("max_thr", C.c_int32), ("thr_down", C.c_int32),
                 ("thr_up", C.c_int32), ("max_time_ms", C.c_int32), ("inh_k", C.c_int32),
-                ("polarity", C.c_int32), ("force_generic", C.c_int32), ("reserved0", C.c_int32),
+                ("polarity", C.c_int32), ("force_generic", C.c_int32), ("drop_silent", C.c_int32),
                 ("history_weight", C.c_double), ("enc", EncParams),
                 ("curr", C.c_void_p), ("ref", C.c_void_p), ("thr", C.c_void_p),
                 ("diff_out", C.c_void_p), ("abs_diff_out", C.c_void_p), ("spikes_out", C.c_void_p),

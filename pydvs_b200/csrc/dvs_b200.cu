@@ -773,6 +773,7 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
   A.upd.hw = p->history_weight; A.upd.hw_is_one = p->history_weight == 1.0; A.upd.div_thr = make_div(p->threshold);
   A.enc = make_enc(&p->enc);
   A.fast_hist = (A.enc.mode == DVS_ENC_RATE || A.enc.mode == DVS_ENC_TIME) && A.enc.n_slots <= 8;
+  A.drop_silent = p->drop_silent != 0;
   A.curr = p->curr; A.ref = p->ref; A.thr = p->thr;
   A.diff_out = p->diff_out; A.abs_out = p->abs_diff_out; A.spk_out = p->spikes_out;
   A.records = p->records; A.tile_counts = p->tile_counts; A.status = p->status;

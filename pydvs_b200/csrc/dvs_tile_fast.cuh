@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
       if (SIMPLE) {
         tp = !neg; tn = neg;
         desc = max(0, (A.enc.n_slots - 1) - (int)__umulhi((unsigned)a, A.enc.dv.magic));  // k, gs:830-832
-        atomicAdd(&hist[(neg ? nh : 0) + desc], 1u);  // fire-and-forget shared-memory reduction (k <= n_slots - 1)
+        if (desc == 0 && A.drop_silent) { tp = false; tn = false; }  // k == 0: in no slot; the record would only be skipped by K3
+        else atomicAdd(&hist[(neg ? nh : 0) + desc], 1u);  // fire-and-forget shared-memory reduction (k <= n_slots - 1)
       } else {
         split_px(neg ? -1 : 1, A.polarity, A.uncoded, tp, tn);
         if (tp || tn) desc = hist_add(A, hist, nh, a, tp, hp, hn, status, /*allow_regs=*/false);

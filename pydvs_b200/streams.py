@@ -163,7 +163,8 @@ class StepResult:
 
 class DVSStreams:
     def __init__(self, cfg: DVSConfig, device=None, event_capacity: Optional[int] = None,
-                 debug_planes: bool = False, force_generic: bool = False, pipeline_depth: int = 1):
+                 debug_planes: bool = False, force_generic: bool = False, pipeline_depth: int = 1,
+                 split_lists: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("pydvs_b200 needs a CUDA device (there is no CPU path)")
         self.cfg = cfg = cfg.resolved()
@@ -230,6 +231,9 @@ class DVSStreams:
             self.debug = {n: torch.zeros((self.S, self.H, self.W), dtype=torch.int16, device=dev)
                           for n in ("diff", "abs_diff", "spikes")}
         self.force_generic = bool(force_generic)
+        # split_lists=False: the per-tile record lists only feed the AER expand, so spikes that emit no event
+        # (coded rate: k == 0) need not be recorded; events are identical, split_spikes() is unavailable.
+        self.split_lists = bool(split_lists)
         self._enc = self._make_enc()
         self._params = self._make_params()
         self.frames_done = 0
@@ -261,6 +265,7 @@ class DVSStreams:
         p.thr_down, p.thr_up, p.max_time_ms = int(cfg.threshold_delta_down), int(cfg.threshold_delta_up), int(cfg.max_time_ms)
         p.inh_k, p.polarity, p.history_weight = self.inh_k, int(cfg.polarity), float(cfg.history_weight)
         p.force_generic = int(self.force_generic)
+        p.drop_silent = int(not self.split_lists)
         p.enc = self._enc
         p.ref = self.ref.data_ptr()
         p.thr = self.thr.data_ptr() if self.thr is not None else None
@@ -377,6 +382,8 @@ class DVSStreams:
     def split_spikes(self, stream=0):
         """(neg[3, Nn], pos[3, Np]) of the last step for one stream, as ``split_spikes`` returns
         them (``generate_spikes.pyx:716-719``)."""
+        if not self.split_lists:
+            raise RuntimeError("split_spikes() needs DVSStreams(..., split_lists=True): silent spikes were not recorded")
         tot = self.stream_totals.view(self.S, self.C)[stream, :2].cpu().numpy()
         n_pos, n_neg = int(tot[0]), int(tot[1])
         pos = torch.empty((3, n_pos), dtype=torch.int16, device=self.device)

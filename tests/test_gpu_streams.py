@@ -17,7 +17,8 @@ def _key_params(W, H):
 
 def _run_case(S, H, W, *, output_type="RATE", frames=6, source="random", inh=0, adaptive=False, hw=1.0,
               polarity=2, uncoded=False, frame_dtype="int16", threshold=12, max_time_ms=8, num_bins=None,
-              thr0=None, tile_rows=None, seed=0, lut_bits=(2, 6), ref0=128, debug=True, force_generic=False):
+              thr0=None, tile_rows=None, seed=0, lut_bits=(2, 6), ref0=128, debug=True, force_generic=False,
+              split_lists=True):
     from oracle import oracle as orc
     from pydvs_b200 import DVSConfig, DVSStreams, synth
     import pydvs_b200.generate_spikes as gs
@@ -28,7 +29,7 @@ def _run_case(S, H, W, *, output_type="RATE", frames=6, source="random", inh=0, 
                     inh_area_width=inh, uncoded=uncoded, frame_dtype=frame_dtype, log2_table=lut,
                     threshold0=thr0, tile_rows=tile_rows, ref0=ref0)
     dvs = DVSStreams(cfg, debug_planes=debug, event_capacity=S * H * W * max(8, max_time_ms),
-                     force_generic=force_generic)
+                     force_generic=force_generic, split_lists=split_lists)
     rc = dvs.cfg
     fs, ds, dm = _key_params(W, H)
     pipes = [orc.Pipeline(W, H, mode=ENC[output_type], threshold=threshold, max_time_ms=rc.max_time_ms,
@@ -81,7 +82,7 @@ def _run_case(S, H, W, *, output_type="RATE", frames=6, source="random", inh=0, 
             assert len(got) == len(exp_lists)
             assert got == exp_lists, (t, s, "lists")
             total += sum(len(x) for x in exp_lists)
-            if t == frames - 1:  # split_spikes view of the same step
+            if t == frames - 1 and split_lists:  # split_spikes view of the same step
                 neg, pos = dvs.split_spikes(s)
                 n_e, p_e, _ = O.split_spikes(sp, a, polarity)
                 assert np.array_equal(neg.cpu().numpy(), n_e.view(np.int16))
@@ -163,6 +164,17 @@ def test_degenerate_slot_counts():
     _run_case(2, 16, 64, output_type="TIME", num_bins=1, frames=3, debug=False)
     _run_case(1, 2, 8, frames=3, debug=False)            # a single tile of a single group pair
     _run_case(1, 2, 8, inh=2, frames=3, debug=False)
+
+
+def test_events_are_identical_when_silent_records_are_dropped():
+    # split_lists=False: spikes with k == 0 (no event) are left out of the tile lists by the inlined fast path
+    for kw in (dict(inh=2), dict(inh=0), dict(inh=2, frame_dtype="uint8"), dict(inh=2, source="bar")):
+        dvs = _run_case(2, 32, 128, frames=5, debug=False, split_lists=False, **kw)
+    with pytest.raises(RuntimeError):
+        dvs.split_spikes(0)
+    _run_case(1, 64, 3840, frames=3, inh=2, debug=False, split_lists=False)           # two column blocks per thread
+    _run_case(2, 16, 64, frames=3, output_type="TIME", debug=False, split_lists=False)  # not the inlined path: flag ignored
+    _run_case(2, 16, 64, frames=3, debug=False, split_lists=False, force_generic=True)
 
 
 def test_many_streams_use_the_multi_block_segment_scan():
