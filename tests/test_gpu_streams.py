@@ -172,6 +172,10 @@ def test_events_are_identical_when_silent_records_are_dropped():
         dvs = _run_case(2, 32, 128, frames=5, debug=False, split_lists=False, **kw)
     with pytest.raises(RuntimeError):
         dvs.split_spikes(0)
+    # saturated silent spikes are finished on packed lanes: vary where "silent" (k == 0) and "saturated" start
+    for mt, T in ((3, 12), (16, 12), (8, 3), (8, 30), (1, 12), (2, 100)):
+        _run_case(2, 32, 128, frames=4, inh=2, debug=False, split_lists=False, max_time_ms=mt, threshold=T)
+        _run_case(2, 32, 128, frames=4, inh=0, debug=False, split_lists=False, max_time_ms=mt, threshold=T, seed=3)
     _run_case(1, 64, 3840, frames=3, inh=2, debug=False, split_lists=False)           # two column blocks per thread
     _run_case(2, 16, 64, frames=3, output_type="TIME", debug=False, split_lists=False)  # not the inlined path: flag ignored
     _run_case(2, 16, 64, frames=3, debug=False, split_lists=False, force_generic=True)
