@@ -67,6 +67,8 @@ def parse_args():
     ap.add_argument("--pipeline-depth", type=int, default=1, choices=[1, 2],
                     help="2: double-buffer records/counters/events and run the AER expand of step n on a side "
                          "stream while the tile pass of step n+1 runs (steady-state streaming); 1: in line")
+    ap.add_argument("--k1-variant", default="auto", choices=["auto", "plain", "staged"],
+                    help="auto / plain: one tile per CTA; staged: persistent CTAs fed by cp.async.bulk + mbarrier (opt-in, slower)")
     ap.add_argument("--graph", action="store_true", help="replay the step as one CUDA graph (launch-bound configs)")
     ap.add_argument("--settle", type=int, default=24,
                     help="untimed steps before the warm-up: with inhibition only one pixel of each 2x2 area moves "
@@ -337,6 +339,7 @@ def run_ours(args, wl, rank, local_rank, world):
     per_px_events = (1.0 if wl["inh"] > 1 else 3.0) if args.pattern == "bar" else 3.0
     depth = 1 if args.graph else args.pipeline_depth
     dvs = DVSStreams(cfg, device=device, event_capacity=int(max(1 << 20, S * P * per_px_events)), pipeline_depth=depth,
+                     force_generic={"auto": 0, "plain": 0, "staged": 3}[args.k1_variant],
                      split_lists=False)  # AER events are the output; split_spikes lists are not requested
     ring = make_ring(wl, S, args.ring, args.pattern, args.frame_dtype, device, stream_base)
     torch.cuda.synchronize()

@@ -131,7 +131,8 @@ typedef struct dvs_step_params {
   int32_t max_time_ms;
   int32_t inh_k;            /* local_inhibition area width; <= 1: off                         */
   int32_t polarity;         /* DVS_POL_*                                                      */
-  int32_t force_generic;    /* 1: never take the specialised fast kernel (testing / profiling) */
+  int32_t force_generic;    /* testing / profiling: 1 = never take the specialised fast kernel, 3 = its persistent
+                             * staged form (bulk async copies + mbarrier) whenever the tile shape allows it   */
   int32_t drop_silent;      /* 1: records that emit no event (coded rate, k == 0) may be left out of the
                              * tile lists: identical events, but the lists no longer are split_spikes' output */
   double history_weight;

@@ -774,6 +774,8 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
   A.enc = make_enc(&p->enc);
   A.fast_hist = (A.enc.mode == DVS_ENC_RATE || A.enc.mode == DVS_ENC_TIME) && A.enc.n_slots <= 8;
   A.drop_silent = p->drop_silent != 0;
+  // force_generic == 3: the persistent staged kernel whenever the tile shape allows it (opt-in, see dvs_tile_fast.cuh)
+  A.use_staged = p->force_generic == 3 ? 2 : 0;
   A.curr = p->curr; A.ref = p->ref; A.thr = p->thr;
   A.diff_out = p->diff_out; A.abs_out = p->abs_diff_out; A.spk_out = p->spikes_out;
   A.records = p->records; A.tile_counts = p->tile_counts; A.status = p->status;
@@ -794,7 +796,7 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
   const bool fast = !p->adaptive && upd_ok &&
                     p->threshold >= 2 && p->threshold <= 32767 && p->max_time_ms >= 0 && A.vec_ok &&
                     A.W % 8 == 0 && A.tile_px / 8 <= 1024 && !p->diff_out && !p->abs_diff_out &&
-                    !p->spikes_out && !p->force_generic && p->redo && A.S <= 65535;
+                    !p->spikes_out && p->force_generic != 1 && p->redo && A.S <= 65535;
   A.redo = p->redo;
   if (fast) return u8 ? launch_tile_fast_u8(A, st) : launch_tile_fast_i16(A, st);
   // adaptive fast path: coded rate_adpt rule, no history decay, inhibition off or 2x2 on two-row tiles
@@ -807,7 +809,7 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
                          p->min_thr >= 0 && p->min_thr <= p->max_thr && p->max_thr <= 32767 && p->thr_up >= 0 &&
                          p->thr_up <= 32767 && p->thr_down >= 0 && p->thr_down <= 32767 && A.vec_ok && A.W % 8 == 0 &&
                          A.tile_px / 8 <= 1024 && (k == 1 || (k == 2 && A.tile_rows == 2 && A.H % 2 == 0)) &&
-                         !p->diff_out && !p->abs_diff_out && !p->spikes_out && !p->force_generic && p->redo && A.S <= 65535;
+                         !p->diff_out && !p->abs_diff_out && !p->spikes_out && p->force_generic != 1 && p->redo && A.S <= 65535;
   if (fast_adpt) return u8 ? launch_tile_fast_u8_adpt(A, st) : launch_tile_fast_i16_adpt(A, st);
   if (u8) return p->adaptive ? launch_tile_pass_u8_adpt(A, st) : launch_tile_pass_u8(A, st);
   return p->adaptive ? launch_tile_pass_i16_adpt(A, st) : launch_tile_pass_i16(A, st);

@@ -38,13 +38,16 @@ constexpr int kFastCap = 2048;  // work-list capacity; denser tiles go to the ge
 // update_reference_rate_adpt gs:256-297): the plane is read with the frame, compared lane-wise, advanced
 // (+up where the pixel spikes after inhibition, -down elsewhere, clipped) on packed lanes and written back
 // for every pixel (10 B/px); the division abs_diff // threshold only happens for candidates.
-template <int SRC, int JH, bool PAIR, bool SIMPLE, bool ADAPT = false>
-__global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(const __grid_constant__ TileArgs A) {
+// One tile.  STAGED: the tile's frame / reference rows were brought into shared memory by a bulk async copy
+// (st_cur / st_ref); after the first barrier every thread holds its pixels in registers, so the stage buffer
+// is dead and doubles as work list + record staging (smem_raw points at it; `ctl` holds wtot / hist).
+template <int SRC, int JH, bool PAIR, bool SIMPLE, bool ADAPT, bool STAGED>
+DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigned char *smem_raw, unsigned char *ctl,
+                    const unsigned char *st_cur, const unsigned char *st_ref) {
   constexpr int J = PAIR ? 2 * JH : JH;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
   uint2 *rec_sm = reinterpret_cast<uint2 *>(smem_raw + kFastCap * 4);
-  uint32_t *wtot = reinterpret_cast<uint32_t *>(smem_raw + kFastCap * 12);
+  uint32_t *wtot = reinterpret_cast<uint32_t *>(ctl);
   uint16_t *wl_thr = reinterpret_cast<uint16_t *>(wtot + 128 + 2 * (A.enc.mode == DVS_ENC_NONE ? 0 : A.enc.n_slots + 1) + 8);  // ADAPT
   uint8_t *tr_lut = reinterpret_cast<uint8_t *>(wl_thr + (ADAPT ? kFastCap : 0));  // history_weight != 1: trunc(hw * r), r in [0, 255]
   const bool decay = !SIMPLE && A.upd.hw_is_one == 0;  // (SIMPLE implies plain rate update, no decay) 0 <= history_weight < 1 (host-checked): every pixel's reference moves
@@ -52,7 +55,6 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
   const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
-  const int t_idx = blockIdx.x, s_idx = blockIdx.y;
   const int tile = s_idx * A.tiles_per_stream + t_idx;
   const int row0 = t_idx * A.tile_rows;
   const int npx = min(A.tile_rows, A.H - row0) * A.W;  // multiple of 8 (host-checked)
@@ -81,14 +83,14 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
         t_pk[j][0] = t.x; t_pk[j][1] = t.y; t_pk[j][2] = t.z; t_pk[j][3] = t.w;
       }
       if (SRC == SRC_U8) {
-        const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(cur_t + q0));
+        const uint2 v = STAGED ? *reinterpret_cast<const uint2 *>(st_cur + q0) : __ldcs(reinterpret_cast<const uint2 *>(cur_t + q0));
         c_pk[j][0] = __byte_perm(v.x, 0, 0x4140); c_pk[j][1] = __byte_perm(v.x, 0, 0x4342);
         c_pk[j][2] = __byte_perm(v.y, 0, 0x4140); c_pk[j][3] = __byte_perm(v.y, 0, 0x4342);
       } else {
-        const uint4 v = ld16_stream(cur_t + 2 * q0);
+        const uint4 v = STAGED ? *reinterpret_cast<const uint4 *>(st_cur + 2 * q0) : ld16_stream(cur_t + 2 * q0);
         c_pk[j][0] = v.x; c_pk[j][1] = v.y; c_pk[j][2] = v.z; c_pk[j][3] = v.w;
       }
-      const uint4 r = ld16(ref_t + q0);
+      const uint4 r = STAGED ? *reinterpret_cast<const uint4 *>(st_ref + 2 * q0) : ld16(ref_t + q0);
       r_pk[j][0] = r.x; r_pk[j][1] = r.y; r_pk[j][2] = r.z; r_pk[j][3] = r.w;
     }
   }
@@ -353,6 +355,93 @@ __global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(cons
 }
 
 template <int SRC, int JH, bool PAIR, bool SIMPLE, bool ADAPT = false>
+__global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(const __grid_constant__ TileArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  fast2_tile<SRC, JH, PAIR, SIMPLE, ADAPT, false>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + kFastCap * 12,
+                                                  nullptr, nullptr);
+}
+
+// ---- persistent, staged variant (opt-in: dvs_step_params.force_generic == 3) -----------------------
+// Measured on 4K x 256 streams: 2.61 ms against 2.08 ms for one tile per CTA (3 CTAs/SM = 24 warps cannot cover
+// the barrier / ALU latencies of the compute phases that 5 CTAs/SM = 40 warps do; a single-stage form at 4 CTAs/SM
+// took 2.97 ms).  Kept for shapes / future parts where DRAM latency rather than issue slots is the limit.
+// One CTA per resident slot (grid = SMs x CTAs/SM) walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The rows of
+// tile k+1 (frame and reference: two contiguous runs of global memory) are fetched by one elected thread with
+// cp.async.bulk into the other half of a two-stage shared-memory ring while tile k is processed; completion is
+// signalled through an mbarrier (expect_tx / complete_tx), so no warp ever waits on DRAM with registers reserved
+// for in-flight loads.  shared memory: [stage 0][stage 1][wtot 128 u32][hist][tr_lut][2 mbarriers].
+DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DEV void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DEV void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEV void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+DEV void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+#ifndef FAST2S_MINB
+#define FAST2S_MINB 3
+#endif
+template <int SRC, int JH, bool PAIR, bool SIMPLE>
+__global__ void __launch_bounds__(256, FAST2S_MINB) k_tile_fast2s(const __grid_constant__ TileArgs A, const int stage_bytes) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char *ctl = smem_raw + 2 * stage_bytes;
+  const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(ctl + (((128 + 2 * nh + 8) * 4 + 256 + 15) & ~15));
+  const long long n_tiles = (long long)A.S * A.tiles_per_stream;
+  const int elem = SRC == SRC_U8 ? 1 : 2;
+  const int cur_bytes_max = A.tile_px * elem;  // the reference rows follow the frame rows inside a stage
+
+  auto issue = [&](long long tile, int stage) {  // one thread
+    const int s_idx = (int)(tile / A.tiles_per_stream), t_idx = (int)(tile - (long long)s_idx * A.tiles_per_stream);
+    const int row0 = t_idx * A.tile_rows;
+    const int npx = min(A.tile_rows, A.H - row0) * A.W;
+    const size_t plane_off = ((size_t)s_idx * A.H + row0) * A.W;
+    unsigned char *dst = smem_raw + (size_t)stage * stage_bytes;
+    mbar_expect_tx(&bars[stage], (uint32_t)(npx * (elem + 2)));
+    bulk_g2s(dst, static_cast<const unsigned char *>(A.curr) + plane_off * elem, (uint32_t)(npx * elem), &bars[stage]);
+    bulk_g2s(dst + cur_bytes_max, reinterpret_cast<const unsigned char *>(A.ref + plane_off), (uint32_t)(npx * 2), &bars[stage]);
+  };
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  long long tile = blockIdx.x;
+  if (threadIdx.x == 0 && tile < n_tiles) issue(tile, 0);
+  for (int k = 0; tile < n_tiles; ++k, tile += gridDim.x) {
+    const int stage = k & 1;
+    if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) {
+      // the other stage was last touched through the generic proxy (work list / records of tile k - 1)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(tile + gridDim.x, stage ^ 1);
+    }
+    mbar_wait(&bars[stage], (uint32_t)((k >> 1) & 1));
+    const int s_idx = (int)(tile / A.tiles_per_stream), t_idx = (int)(tile - (long long)s_idx * A.tiles_per_stream);
+    unsigned char *st = smem_raw + (size_t)stage * stage_bytes;
+    fast2_tile<SRC, JH, PAIR, SIMPLE, false, true>(A, t_idx, s_idx, st, ctl, st, st + cur_bytes_max);
+    __syncthreads();  // tile k is finished with its stage, wtot and hist before anything of tile k + 1 touches them
+  }
+}
+
+template <int SRC, int JH, bool PAIR, bool SIMPLE, bool ADAPT = false>
 static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
   auto k = k_tile_fast2<SRC, JH, PAIR, SIMPLE, ADAPT>;
   const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
@@ -362,7 +451,27 @@ static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
     return set_error((int)e, cudaGetErrorString(e));
   if ((e = cudaMemsetAsync(A.redo, 0, sizeof(int32_t), st)) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
   const long long tiles = (long long)A.S * A.tiles_per_stream;
-  k<<<dim3((unsigned)A.tiles_per_stream, (unsigned)A.S), bd, smem, st>>>(A);
+  bool staged = false;
+  if constexpr (!ADAPT && PAIR) {
+    // persistent staged kernel: worth it once every resident CTA has several tiles to walk
+    const int stage_bytes = (A.tile_px * ((SRC == SRC_U8 ? 1 : 2) + 2) + 127) & ~127;
+    const size_t smem_s = 2 * (size_t)stage_bytes + (((128 + 2 * nh + 8) * 4 + 256 + 15) & ~15) + 16;
+    static int sm_count = 0;
+    if (sm_count == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const long long resident = (long long)sm_count * FAST2S_MINB;
+    if (A.use_staged == 2 && stage_bytes >= kFastCap * 12 && smem_s <= 72 * 1024) {  // opt-in: measured slower than one tile per CTA
+      auto ks = k_tile_fast2s<SRC, JH, PAIR, SIMPLE>;
+      if ((e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)) != cudaSuccess)
+        return set_error((int)e, cudaGetErrorString(e));
+      ks<<<(unsigned)resident, bd, smem_s, st>>>(A, stage_bytes);
+      staged = true;
+    }
+  }
+  if (!staged) k<<<dim3((unsigned)A.tiles_per_stream, (unsigned)A.S), bd, smem, st>>>(A);
   if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
   // generic body over the (normally zero) declined tiles; its group-to-thread mapping is the linear one
   constexpr int JR = (PAIR ? 2 * JH : JH) > 1 ? 4 : 1;

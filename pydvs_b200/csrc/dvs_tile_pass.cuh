@@ -15,7 +15,7 @@ enum { INH_NONE = 0, INH_K2 = 2, INH_GENERIC = -1 };
 
 struct TileArgs {
   int S, H, W, tile_rows, tiles_per_stream, tile_px, C;
-  int adaptive, polarity, uncoded, inh_k, vec_ok, fast_hist, drop_silent;
+  int adaptive, polarity, uncoded, inh_k, vec_ok, fast_hist, drop_silent, use_staged;
   int thr_scalar;
   unsigned inv_w;          // ceil(2^32 / W): q / W == umulhi(q, inv_w) for q < 32768
   UpdateArgs upd;

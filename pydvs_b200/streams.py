@@ -230,7 +230,7 @@ class DVSStreams:
         if debug_planes:
             self.debug = {n: torch.zeros((self.S, self.H, self.W), dtype=torch.int16, device=dev)
                           for n in ("diff", "abs_diff", "spikes")}
-        self.force_generic = bool(force_generic)
+        self.force_generic = int(force_generic)  # 0/1; 3 = persistent staged fast kernel (see dvs_step_params)
         # split_lists=False: the per-tile record lists only feed the AER expand, so spikes that emit no event
         # (coded rate: k == 0) need not be recorded; events are identical, split_spikes() is unavailable.
         self.split_lists = bool(split_lists)

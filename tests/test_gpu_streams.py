@@ -181,6 +181,19 @@ def test_events_are_identical_when_silent_records_are_dropped():
     _run_case(2, 16, 64, frames=3, debug=False, split_lists=False, force_generic=True)
 
 
+def test_persistent_staged_kernel():
+    """k_tile_fast2s (bulk async copies into a two-stage shared-memory ring, persistent CTAs; opt-in) needs tiles of at
+    least 24 KB; force it on small problems (more CTAs than tiles, one tile per CTA, several tiles per CTA)."""
+    for S, H in ((1, 8), (2, 64), (5, 720)):
+        for kw in (dict(), dict(split_lists=False), dict(frame_dtype="uint8"), dict(hw=0.9), dict(polarity=0),
+                   dict(output_type="TIME", num_bins=4, max_time_ms=4)):
+            if S == 5 and kw and "split_lists" not in kw:
+                continue
+            _run_case(S, H, 3840, frames=3, inh=2, debug=False, force_generic=3, **kw)
+    _run_case(3, 32, 3072, frames=3, inh=2, debug=False, force_generic=3, source="bar")
+    _run_case(2, 16, 3840, frames=3, inh=2, debug=False, force_generic=3, source="wide")   # declined tiles -> redo list
+
+
 def test_many_streams_use_the_multi_block_segment_scan():
     # S * 2 * n_slots > 8192 segments: stream sums / scan / fill run as three launches
     _run_case(1100, 8, 16, frames=2, debug=False, threshold=3)
