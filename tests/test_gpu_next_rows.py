@@ -251,3 +251,48 @@ def test_traverse_and_fade_random_vs_oracle():
             out = fs.fade_images(_cu(imgs), idx, fn, hf, bg=11).cpu().numpy()
             for s in range(S):
                 assert np.array_equal(out[s], fo.fade_image(imgs[idx[s]], int(fn[s]), hf, 11)), (H, W, hf, s)
+
+
+# ---- deterministic batched VirtualCam --------------------------------------------------------------------
+@pytest.mark.parametrize("behaviour", ["SACCADE", "TRAVERSE", "FADE", "NONE"])
+@pytest.mark.parametrize("with_mask", [False, True])
+def test_virtual_cam_schedule_matches_scalar_restatement(behaviour, with_mask):
+    from oracle.virtual_cam_oracle import VirtualCamOracle
+    from pydvs_b200.virtual_cam import VirtualCam
+    rng = np.random.default_rng(4)
+    N, H, W, S = 3, 32, 32, 5
+    imgs = rng.integers(0, 256, (N, H, W)).astype(np.int16)
+    mask = rng.uniform(0, 1, (H, W)) if with_mask else None
+    start = np.array([0, 1, 2, 1, 0])
+    kw = dict(fps=30, image_on_time_ms=400, inter_off_time_ms=100, max_saccade_distance=2,
+              frames_per_microsaccade=2, max_cycles=2, background_gray=9)
+    cam = VirtualCam(_cu(imgs), behaviour=behaviour, fade_mask=mask, streams=S, start_index=start, seed=11, **kw)
+    refs = [VirtualCamOracle(imgs, behaviour, fade_mask=mask, start_index=int(start[s]),
+                             rng=np.random.RandomState(11 + s), **kw) for s in range(S)]
+    n_valid = 0
+    for step in range(140):
+        ok, frames = cam.read()
+        host = frames.cpu().numpy()
+        for s in range(S):
+            ok_ref, img = refs[s].read()
+            assert ok == ok_ref, (step, s)
+            assert np.array_equal(host[s], img), (behaviour, step, s)
+        n_valid += ok
+        if not ok and behaviour != "NONE":
+            break
+    assert n_valid > 50
+    if behaviour != "NONE":
+        assert not ok   # max_cycles reached: the camera reports end of stream and serves the background
+
+
+def test_virtual_cam_attention_runs_and_recentres():
+    from pydvs_b200.virtual_cam import VirtualCam
+    rng = np.random.default_rng(8)
+    imgs = rng.integers(0, 256, (2, 32, 32)).astype(np.int16)
+    cam = VirtualCam(_cu(imgs), behaviour="ATTENTION", fps=30, image_on_time_ms=2000, frames_per_saccade=5,
+                     streams=3, seed=2)
+    ref = torch.full((3, 32, 32), 128, dtype=torch.int16, device="cuda")
+    for step in range(12):
+        ok, frames = cam.read(ref)
+        assert ok and frames.shape == (3, 32, 32) and frames.dtype == torch.int16
+        assert np.abs(cam.center).max() <= 16 + 12
