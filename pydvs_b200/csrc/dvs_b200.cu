@@ -504,6 +504,37 @@ __global__ void __launch_bounds__(256) k_local_inhibition(int16_t *__restrict__ 
       if (rr != br || cc != bc) spikes[o + (size_t)rr * W + cc] = 0;
 }
 
+// k == 2 on 16-byte aligned rows with W % 8 == 0: a thread owns 8 columns of a row pair (four 2x2 areas), reads
+// abs_diff and spikes with 16-byte loads and only writes the rows back when some spike was actually removed.
+__global__ void __launch_bounds__(256) k_local_inhibition2_vec(int16_t *__restrict__ spikes,
+                                                               const int16_t *__restrict__ abs_diff, long long n_pairs,
+                                                               int W) {
+  const int gpr = W >> 3;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_pairs * gpr) return;
+  const long long pair = g / gpr;  // row pairs are contiguous over streams because H is even
+  const int cg = (int)(g - pair * gpr);
+  const size_t o = (size_t)pair * 2 * W + (size_t)cg * 8;
+  const uint4 su = ld16(spikes + o), sl = ld16(spikes + o + W);
+  if ((su.x | su.y | su.z | su.w | sl.x | sl.y | sl.z | sl.w) == 0u) return;  // nothing to inhibit
+  const uint4 au = ld16(abs_diff + o), al = ld16(abs_diff + o + W);
+  const uint32_t a_u[4] = {au.x, au.y, au.z, au.w}, a_l[4] = {al.x, al.y, al.z, al.w};
+  uint32_t s_u[4] = {su.x, su.y, su.z, su.w}, s_l[4] = {sl.x, sl.y, sl.z, sl.w};
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int t00 = (int16_t)(a_u[w] & 0xffffu), t01 = (int16_t)(a_u[w] >> 16);
+    const int t10 = (int16_t)(a_l[w] & 0xffffu), t11 = (int16_t)(a_l[w] >> 16);
+    int best = t00, bi = 0;  // argmax gs:118-132: first maximum in row-major order, strict '>'
+    if (t01 > best) { best = t01; bi = 1; }
+    if (t10 > best) { best = t10; bi = 2; }
+    if (t11 > best) { best = t11; bi = 3; }
+    s_u[w] &= bi == 0 ? 0x0000ffffu : (bi == 1 ? 0xffff0000u : 0u);
+    s_l[w] &= bi == 2 ? 0x0000ffffu : (bi == 3 ? 0xffff0000u : 0u);
+  }
+  if ((s_u[0] ^ su.x) | (s_u[1] ^ su.y) | (s_u[2] ^ su.z) | (s_u[3] ^ su.w)) st16(spikes + o, s_u);
+  if ((s_l[0] ^ sl.x) | (s_l[1] ^ sl.y) | (s_l[2] ^ sl.z) | (s_l[3] ^ sl.w)) st16(spikes + o + W, s_l);
+}
+
 __global__ void __launch_bounds__(256) k_update_reference(const __grid_constant__ UpdateArgs U,
                                                           const int16_t *__restrict__ abs_diff,
                                                           const int16_t *__restrict__ spikes,
@@ -521,6 +552,35 @@ __global__ void __launch_bounds__(256) k_update_reference(const __grid_constant_
   load8_i16(ref_in, q0, nv, vec, r);
   if (adpt) load8_i16(thr, q0, nv, vec, t);
   unsigned status = 0;
+  if (U.mode == DVS_UPD_RATE && U.hw_is_one && U.div_thr.T >= 2 && nv == 8) {
+    // update_reference_rate gs:244-249 with history_weight == 1 and a scalar threshold >= 2, word by word (two
+    // pixels): quiet words reduce to clip(ref, 0, 255) on packed signed lanes; a spiking pixel with abs_diff >= 0
+    // takes the magic-number division; anything else goes through the general rule.  Every int16 wrap is kept.
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      if (s[w] == 0u) {
+        rn[w] = __vmins2(__vmaxs2(r[w], 0u), 0x00ff00ffu);
+        continue;
+      }
+      uint32_t out = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int av = (int)(short)(a[w] >> (16 * h)), sv = (int)(short)(s[w] >> (16 * h)), rv = (int)(short)(r[w] >> (16 * h));
+        int v;
+        if (av >= 0) {
+          const int nq = min((int)__umulhi((unsigned)av, U.div_thr.magic), U.max_time_ms);  // clip(q, 0, max): q >= 0 here
+          v = clip(w16(rv + w16(w16(nq * sv) * U.threshold)), 0, 255);
+        } else {
+          int th_state = 0, th_ret = 0;
+          v = update_px(U, av, sv, rv, th_state, th_ret, status);
+        }
+        out |= ((uint32_t)v & 0xffffu) << (16 * h);
+      }
+      rn[w] = out;
+    }
+    store8_i16(ref_out, q0, nv, vec, rn);
+    return;
+  }
 #pragma unroll
   for (int p = 0; p < 8; ++p) {
     if (p < nv) {
@@ -949,6 +1009,11 @@ int dvs_local_inhibition_i16(int16_t *spikes, const int16_t *abs_diff, int32_t S
   if (W % k || H % k) return fail(DVS_ERR_INVALID_ARGUMENT, "inhibition needs W and H divisible by inh_width (reference: IndexError)");
   if (k == 1) return DVS_OK;
   const long long n_areas = (long long)S * (W / k) * (H / k);
+  if (k == 2 && W % 8 == 0 && aligned16(spikes) && aligned16(abs_diff)) {
+    const long long n_pairs = (long long)S * (H / 2), n_thr = n_pairs * (W / 8);
+    k_local_inhibition2_vec<<<(unsigned)((n_thr + 255) / 256), 256, 0, as_stream(stream)>>>(spikes, abs_diff, n_pairs, W);
+    return check_launch("k_local_inhibition2_vec");
+  }
   k_local_inhibition<<<(unsigned)((n_areas + 255) / 256), 256, 0, as_stream(stream)>>>(spikes, abs_diff, S, H, W, k);
   return check_launch("k_local_inhibition");
 }

@@ -131,6 +131,44 @@ def test_update_reference_variants(uncoded, shape):
                 assert t_got is t_gpu
 
 
+def test_update_reference_rate_on_arbitrary_int16_planes():
+    """The unfused kernels take whatever int16 planes the caller hands them: negative abs_diff, spikes other than
+    -1/0/1, references outside [0, 255], products that wrap (the specialised rate path keeps every int16 wrap)."""
+    m, O = _mods(False)
+    rng = np.random.default_rng(21)
+    for shape in ((16, 24), (33, 17), (64, 128)):
+        for T, mt in ((12, 8), (2, 30000), (300, 200), (7, -3), (32767, 5)):
+            a = rng.integers(-32768, 32768, shape).astype(np.int16)
+            s = rng.integers(-4, 5, shape).astype(np.int16)
+            s[rng.integers(0, 2, shape) == 0] = 0
+            r = rng.integers(-400, 700, shape).astype(np.int16)
+            for hw in (1.0, 0.5):
+                with np.errstate(all="ignore"):
+                    exp = O.update_reference_rate(a, s, r, T, mt, hw)
+                assert np.array_equal(_np(m.update_reference_rate(_cu(a), _cu(s), _cu(r), T, mt, hw)), exp), (shape, T, mt, hw)
+
+
+def test_local_inhibition_on_arbitrary_int16_planes():
+    m, O = _mods(False)
+    rng = np.random.default_rng(22)
+    for shape in ((16, 24), (64, 128), (6, 10), (8, 4096)):
+        a = rng.integers(-50, 50, shape).astype(np.int16)      # ties and negative values: first maximum wins
+        s = rng.integers(-2, 3, shape).astype(np.int16)
+        s[rng.integers(0, 3, shape) == 0] = 0
+        exp = s.copy()
+        O.local_inhibition(exp, a, None, shape[1], shape[0], 2)
+        got = _cu(s)
+        out = m.local_inhibition(got, _cu(a), None, shape[1], shape[0], 2)
+        assert out is got and np.array_equal(_np(got), exp), shape
+        batch_s, batch_a = np.stack([s, s[::-1].copy()]), np.stack([a, a[::-1].copy()])   # [S, H, W]
+        exp_b = batch_s.copy()
+        for i in range(2):
+            O.local_inhibition(exp_b[i], batch_a[i], None, shape[1], shape[0], 2)
+        got_b = _cu(batch_s)
+        m.local_inhibition(got_b, _cu(batch_a), None, shape[1], shape[0], 2)
+        assert np.array_equal(_np(got_b), exp_b), shape
+
+
 def test_update_reference_lut_overrun_raises():
     m, O = _mods(False)
     a = np.full((4, 8), 200, dtype=np.int16)
