@@ -104,7 +104,14 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   const uint32_t kadd = (uint32_t)(0x7fff - T) * 0x00010001u;  // bit 15 of (a + kadd) <=> a > T
   uint32_t flags8[J];
   uint32_t rng = 0, cnt_lo = 0, cnt_hi = 0;  // counts of groups (0,1) and (2,3), 16-bit fields
-  uint32_t a_pk[J][4];
+  // abs_diff of a word of two pixels, kept only where the pixel spikes (abs_diff * spikes, gs:73-75); recomputed
+  // where it is needed instead of being held in registers across the phases
+  auto masked_abs = [&](int j, int w) -> uint32_t {
+    const uint32_t c = c_pk[j][w], r = r_pk[j][w];
+    const uint32_t a = __vmaxu2(c, r) - __vminu2(c, r);
+    const uint32_t f = ADAPT ? ~((t_pk[ADAPT ? j : 0][w] | 0x80008000u) - a) & 0x80008000u : (a + kadd) & 0x80008000u;
+    return a & ((f >> 15) * 0xffffu);
+  };
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     flags8[j] = 0;
@@ -116,17 +123,13 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       const uint32_t a = __vmaxu2(c, r) - __vminu2(c, r);  // no borrow: max >= min lane-wise
       if (ADAPT) fl[w] = ~((t_pk[j][w] | 0x80008000u) - a) & 0x80008000u;  // a > threshold lane-wise (both < 2^15)
       else fl[w] = (a + kadd) & 0x80008000u;                 // spike flags at bits 15 / 31
-      a_pk[j][w] = a;
     }
     if (ADAPT) rng |= ((t_pk[j][0] | t_pk[j][1] | t_pk[j][2]) | t_pk[j][3]) & 0x80008000u ? 0xFF00u : 0u;  // negative threshold
     rng |= (r_pk[j][0] | r_pk[j][1] | r_pk[j][2]) | r_pk[j][3];
     if (SRC != SRC_U8) rng |= (c_pk[j][0] | c_pk[j][1] | c_pk[j][2]) | c_pk[j][3];
     if (fl[0] | fl[1] | fl[2] | fl[3]) {
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        a_pk[j][w] &= (fl[w] >> 15) * 0xffffu;  // abs_diff * spikes
-        flags8[j] |= (((fl[w] >> 15) & 1u) | ((fl[w] >> 30) & 2u)) << (2 * w);
-      }
+      for (int w = 0; w < 4; ++w) flags8[j] |= (((fl[w] >> 15) & 1u) | ((fl[w] >> 30) & 2u)) << (2 * w);
     }
   }
   if (PAIR) {
@@ -139,7 +142,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       uint32_t ku = 0, kl = 0;
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
-        const uint32_t up = flags8[ju] ? a_pk[ju][w] : 0u, lo = flags8[jl] ? a_pk[jl][w] : 0u;
+        const uint32_t up = flags8[ju] ? masked_abs(ju, w) : 0u, lo = flags8[jl] ? masked_abs(jl, w) : 0u;
         const int t00 = up & 0xffff, t01 = up >> 16, t10 = lo & 0xffff, t11 = lo >> 16;
         int best = t00, bi = 0;
         if (t01 > best) { best = t01; bi = 1; }
