@@ -37,6 +37,37 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.StepParams) == 16 + 14 * 4 + 8 + 32 + 10 * 8
 
 
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """A C99 translation unit that includes the header, checks the struct sizes the ctypes binding assumes and calls
+    two entry points that need no GPU links against libpydvs_b200.so and runs (what a cgo / JNI / FFI user does)."""
+    import shutil
+    import subprocess
+    from pydvs_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text("""
+#include <stdio.h>
+#include "pydvs_b200.h"
+int main(void) {
+  if (sizeof(dvs_step_params) != %d || sizeof(dvs_enc_params) != %d || sizeof(dvs_tiling) != %d) return 2;
+  if (sizeof(dvs_nvs_params) != %d || sizeof(dvs_key_list) != %d || sizeof(dvs_event) != 8 || sizeof(dvs_record) != 8) return 3;
+  if (dvs_abi_version() != DVS_ABI_VERSION) return 4;
+  if (dvs_step_fused(NULL, NULL) != DVS_ERR_INVALID_ARGUMENT) return 5;
+  if (dvs_choose_tile_rows(256, 2160, 3840, 2) != 2) return 6;
+  puts(dvs_last_error_string());
+  return 0;
+}
+""" % (ctypes.sizeof(_lib.StepParams), ctypes.sizeof(_lib.EncParams), ctypes.sizeof(_lib.Tiling),
+       ctypes.sizeof(_lib.NvsParams), ctypes.sizeof(_lib.KeyList)))
+    exe = tmp_path / "abi"
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-L", lib_dir, "-lpydvs_b200", "-Wl,-rpath," + lib_dir, "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+
+
 def test_choose_tile_rows_and_argument_errors_without_a_gpu():
     from pydvs_b200 import _lib
     lib = _lib.lib
