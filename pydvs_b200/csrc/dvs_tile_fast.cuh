@@ -254,26 +254,54 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     // entry: tile-local pixel index (13 bits) | reference << 13 (8 bits) | abs_diff << 21 (8 bits) | negative << 29
     const uint32_t ent_ex = ent_in - ent;
     const uint32_t ex_lo = in_lo - cnt_lo, ex_hi = in_hi - cnt_hi;
+    auto entry_of = [&](int q, int c, int r) -> uint32_t {
+      // the entry carries the reference the update starts from: trunc(history_weight * r)
+      return (uint32_t)q | ((uint32_t)(decay ? (int)tr_lut[r] : r) << 13) | ((uint32_t)(c < r ? r - c : c - r) << 21) |
+             (c < r ? 1u << 29 : 0u);
+    };
+    uint32_t pos_of[J];
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const uint32_t base = __shfl_sync(kFull, ent_ex, j * NW + warp);
-      if (flags8[j] == 0) continue;
-      const int q0 = q0_of(j);
-      uint32_t pos = base + (((j < 2 ? ex_lo : ex_hi) >> (16 * (j & 1))) & 0xffffu);
-      const unsigned long long c_lo = ((unsigned long long)c_pk[j][1] << 32) | c_pk[j][0], c_hi = ((unsigned long long)c_pk[j][3] << 32) | c_pk[j][2];
-      const unsigned long long r_lo = ((unsigned long long)r_pk[j][1] << 32) | r_pk[j][0], r_hi = ((unsigned long long)r_pk[j][3] << 32) | r_pk[j][2];
-      for (uint32_t m = flags8[j]; m; m &= m - 1) {  // candidates only (at most 4 per group after 2x2 inhibition)
-        const int p = __ffs(m) - 1;
-        {
+    for (int j = 0; j < J; ++j)
+      pos_of[j] = __shfl_sync(kFull, ent_ex, j * NW + warp) + (((j < 2 ? ex_lo : ex_hi) >> (16 * (j & 1))) & 0xffffu);
+    if (PAIR) {
+      // after the 2x2 inhibition an area (word w of the upper and of the lower row group) holds at most one
+      // candidate: walk the four areas of a column block once, instead of the set bits of each row group
+#pragma unroll
+      for (int h = 0; h < JH; ++h) {
+        const int ju = h, jl = JH + h;
+        if ((flags8[ju] | flags8[jl]) == 0) continue;
+        const int qu = q0_of(ju), ql = q0_of(jl);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t bu = (flags8[ju] >> (2 * w)) & 3u, bl = (flags8[jl] >> (2 * w)) & 3u;
+          if ((bu | bl) == 0) continue;
+          const bool up = bu != 0;
+          const int half = (int)((up ? bu : bl) >> 1), sh = 16 * half;
+          const int c = (int)(((up ? c_pk[ju][w] : c_pk[jl][w]) >> sh) & 0xffffu);
+          const int r = (int)(((up ? r_pk[ju][w] : r_pk[jl][w]) >> sh) & 0xffffu);
+          const uint32_t pos = up ? pos_of[ju] : pos_of[jl];
+          if (ADAPT) wl_thr[pos] = (uint16_t)((up ? t_pk[ADAPT ? ju : 0][w] : t_pk[ADAPT ? jl : 0][w]) >> sh);
+          wl[pos] = entry_of((up ? qu : ql) + 2 * w + half, c, r);
+          if (up) pos_of[ju] = pos + 1; else pos_of[jl] = pos + 1;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        if (flags8[j] == 0) continue;
+        const int q0 = q0_of(j);
+        uint32_t pos = pos_of[j];
+        const unsigned long long c_lo = ((unsigned long long)c_pk[j][1] << 32) | c_pk[j][0], c_hi = ((unsigned long long)c_pk[j][3] << 32) | c_pk[j][2];
+        const unsigned long long r_lo = ((unsigned long long)r_pk[j][1] << 32) | r_pk[j][0], r_hi = ((unsigned long long)r_pk[j][3] << 32) | r_pk[j][2];
+        for (uint32_t m = flags8[j]; m; m &= m - 1) {  // candidates only
+          const int p = __ffs(m) - 1;
           const int sh = 16 * (p & 3);
           const int c = (int)(((p < 4 ? c_lo : c_hi) >> sh) & 0xffff), r = (int)(((p < 4 ? r_lo : r_hi) >> sh) & 0xffff);
           if (ADAPT) {
             const unsigned long long t_lo = ((unsigned long long)t_pk[j][1] << 32) | t_pk[j][0], t_hi = ((unsigned long long)t_pk[j][3] << 32) | t_pk[j][2];
             wl_thr[pos] = (uint16_t)((p < 4 ? t_lo : t_hi) >> sh);
           }
-          // the entry carries the reference the update starts from: trunc(history_weight * r)
-          wl[pos++] = (uint32_t)(q0 + p) | ((uint32_t)(decay ? (int)tr_lut[r] : r) << 13) |
-                      ((uint32_t)(c < r ? r - c : c - r) << 21) | (c < r ? 1u << 29 : 0u);
+          wl[pos++] = entry_of(q0 + p, c, r);
         }
       }
     }
