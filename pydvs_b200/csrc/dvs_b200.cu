@@ -299,6 +299,32 @@ __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ ExpandAr
         my_base[j] = (uint32_t)(A.seg_offsets[((long long)s * A.enc.n_slots + j) * 2 + my_pol] - stream_base) +
                      A.tile_excl[((size_t)s * A.C + 2 + 2 * j + my_pol) * A.tps + my_t];
     }
+    // Tasks with a handful of records (the usual case on sparse frames: one or two per tile) are expanded by
+    // their own lane, 32 tasks at a time, instead of occupying the whole warp one after the other.
+    constexpr int kSmallTask = 4;
+    if (__any_sync(kFull, my_n > 0 && my_n <= kSmallTask)) {
+      if (my_n > 0 && my_n <= kSmallTask) {
+        const uint32_t pb = (my_pol ? 0xffffu : 1u) << 16;
+        for (int i = 0; i < my_n; ++i) {
+          const uint2 r = *reinterpret_cast<const uint2 *>(my_rec + i);
+          const int desc = (r.y >> 16) ? (int)(r.y >> 16) - 2 : enc_desc(A.enc, (int)(short)(r.y & 0xffff), my_pol == 0, status);
+          const uint32_t xy = (r.x >> 16) | (r.x << 16);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (A.enc.mode == DVS_ENC_RATE ? desc > j : desc == j) {
+              *reinterpret_cast<uint2 *>(ev_s + my_base[j]) = make_uint2(xy, (uint32_t)j | pb);
+              my_base[j] += 1;
+            }
+          }
+        }
+      }
+      todo = __ballot_sync(kFull, my_n > kSmallTask);
+      if (todo == 0) {
+        status = __reduce_or_sync(kFull, status);
+        if (status && lane == 0 && A.status) atomicOr(A.status, (int)status);
+        return;
+      }
+    }
     int src = __ffs(todo) - 1;
     todo &= todo - 1;
     const dvs_record *rec = reinterpret_cast<const dvs_record *>(__shfl_sync(kFull, (unsigned long long)my_rec, src));
