@@ -63,11 +63,22 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   const unsigned char *const cur_t = static_cast<const unsigned char *>(A.curr) + plane_off * (SRC == SRC_U8 ? 1 : 2);
   const int gpr = A.W >> 3;  // groups of 8 pixels per row
 
-  // group j of this thread starts at tile-local pixel q0(j); PAIR: j = row * JH + column block
+  // group j of this thread starts at tile-local pixel q0(j) = off(j) + 8 * tid, with off(j) uniform over the CTA
+  // (PAIR: j = row * JH + column block), so every address below is "per-thread base + uniform offset"
+  auto off_of = [&](int j) -> int {
+    if (PAIR) return (j / JH) * A.W + (j % JH) * (int)blockDim.x * 8;
+    return j * (int)blockDim.x * 8;
+  };
+  auto in_tile = [&](int j) -> bool {
+    if (PAIR) return (j % JH) * (int)blockDim.x + tid < gpr;
+    return off_of(j) + tid * 8 < npx;
+  };
   auto q0_of = [&](int j) -> int {
-    if (PAIR) { const int cg = (j % JH) * (int)blockDim.x + tid; return cg < gpr ? (j / JH) * A.W + cg * 8 : npx; }
+    if (PAIR) return in_tile(j) ? off_of(j) + tid * 8 : npx;
     return (j * (int)blockDim.x + tid) * 8;
   };
+  const unsigned char *const cur_thread = cur_t + (size_t)tid * 8 * (SRC == SRC_U8 ? 1 : 2);
+  int16_t *const ref_thread = ref_t + tid * 8;
 
   // ---- 1. loads: all 2 * J 128-bit requests of the thread are in flight before first use --------
   uint32_t c_pk[J][4], r_pk[J][4], t_pk[ADAPT ? J : 1][4];
@@ -75,22 +86,22 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   int16_t *const thr_t = ADAPT ? A.thr + plane_off : nullptr;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
-    const int q0 = q0_of(j);
-    have[j] = q0 < npx;
+    const int q0 = PAIR ? off_of(j) + tid * 8 : q0_of(j), off = off_of(j);
+    have[j] = PAIR ? in_tile(j) : q0 < npx;
     if (have[j]) {
       if (ADAPT) {
         const uint4 t = ld16(thr_t + q0);
         t_pk[j][0] = t.x; t_pk[j][1] = t.y; t_pk[j][2] = t.z; t_pk[j][3] = t.w;
       }
       if (SRC == SRC_U8) {
-        const uint2 v = STAGED ? *reinterpret_cast<const uint2 *>(st_cur + q0) : __ldcs(reinterpret_cast<const uint2 *>(cur_t + q0));
+        const uint2 v = STAGED ? *reinterpret_cast<const uint2 *>(st_cur + q0) : __ldcs(reinterpret_cast<const uint2 *>(PAIR ? cur_thread + off : cur_t + q0));
         c_pk[j][0] = __byte_perm(v.x, 0, 0x4140); c_pk[j][1] = __byte_perm(v.x, 0, 0x4342);
         c_pk[j][2] = __byte_perm(v.y, 0, 0x4140); c_pk[j][3] = __byte_perm(v.y, 0, 0x4342);
       } else {
-        const uint4 v = STAGED ? *reinterpret_cast<const uint4 *>(st_cur + 2 * q0) : ld16_stream(cur_t + 2 * q0);
+        const uint4 v = STAGED ? *reinterpret_cast<const uint4 *>(st_cur + 2 * q0) : ld16_stream(PAIR ? cur_thread + 2 * off : cur_t + 2 * q0);
         c_pk[j][0] = v.x; c_pk[j][1] = v.y; c_pk[j][2] = v.z; c_pk[j][3] = v.w;
       }
-      const uint4 r = STAGED ? *reinterpret_cast<const uint4 *>(st_ref + 2 * q0) : ld16(ref_t + q0);
+      const uint4 r = STAGED ? *reinterpret_cast<const uint4 *>(st_ref + 2 * q0) : ld16(PAIR ? ref_thread + off : ref_t + q0);
       r_pk[j][0] = r.x; r_pk[j][1] = r.y; r_pk[j][2] = r.z; r_pk[j][3] = r.w;
     }
   }
