@@ -296,3 +296,43 @@ def test_virtual_cam_attention_runs_and_recentres():
         ok, frames = cam.read(ref)
         assert ok and frames.shape == (3, 32, 32) and frames.dtype == torch.int16
         assert np.abs(cam.center).max() <= 16 + 12
+
+
+# ---- the whole offline flow: frame source -> fused step -> spike files -----------------------------------
+def test_images_to_spike_files_matches_the_cpu_restatement():
+    """examples/images_to_spike_files.py (mnist_to_spikes.py's flow, batched on the GPU) against the same flow on the
+    CPU: scalar VirtualCam restatement -> oracle pipeline -> the reference's writer loop."""
+    import importlib.util
+    import os
+    from oracle import oracle as orc
+    from oracle.virtual_cam_oracle import VirtualCamOracle
+    import pydvs_b200.generate_spikes as gs
+    spec = importlib.util.spec_from_file_location(
+        "_example", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "images_to_spike_files.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    n, frames, fps = 6, 8, 100
+    imgs = ex.blob_images(n, seed=3)
+    writers = ex.convert(imgs, frames=frames, fps=fps, seed=5)
+    frame_ms = int(1000. / fps)
+    lut = gs.generate_log2_table(2, 8)[1]
+    total = 0
+    for s in range(n):
+        cam = VirtualCamOracle(list(imgs), "SACCADE", fps, frames * 1000. / fps * 4, 100, 1, 1, 1, None, 0, s,
+                               np.random.RandomState(5 + s))
+        pipe = orc.Pipeline(32, 32, mode=orc.ENC_TIME_BIN_THR, threshold=12, max_time_ms=frame_ms, num_bins=6,
+                            history_weight=0.99, adaptive=True, min_thr=6, max_thr=168, down=2, up=12, lut=lut,
+                            flag_shift=10, data_shift=5, data_mask=31, ref0=0, thr0=12)
+        lines, t = [], 0
+        for _ in range(frames):
+            ok, frame = cam.read()
+            assert ok
+            t_idx = 0
+            for slot in pipe.step(frame):                  # mnist_to_spikes.py:290-303
+                for key in slot:
+                    lines.append("%s %f" % (key, t + t_idx))
+                t_idx += max(1, frame_ms // 6)
+            t += frame_ms
+        assert writers[s].getvalue() == "\n".join(lines), s
+        total += len(lines)
+    assert total > 100
