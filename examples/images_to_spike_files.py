@@ -18,7 +18,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pydvs_b200 import DVSConfig, DVSStreams  # noqa: E402
-from pydvs_b200.sinks import SpikeFileWriter  # noqa: E402
+from pydvs_b200.sinks import SpikeFileWriter, spike_file_lines_all_streams  # noqa: E402
 from pydvs_b200.virtual_cam import VirtualCam  # noqa: E402
 
 
@@ -59,8 +59,10 @@ def convert(images, frames=10, fps=100, seed=0, key_bits=(10, 5, 31)):
         if not ok:
             break
         res = dvs.step(batch)
+        # one key launch + two device-to-host copies for all images of the frame
+        lines = spike_file_lines_all_streams(res, flag_shift, data_shift, data_mask, writers[0].t, writers[0].t_bin_ms)
         for s in range(n):
-            writers[s].add_frame(res.spike_lists(s, flag_shift, data_shift, data_mask))
+            writers[s].add_lines(lines[s])
     return writers
 
 

@@ -49,6 +49,11 @@ class SpikeFileWriter:
         self.lines += spike_file_lines(lists, self.t, self.t_bin_ms)
         self.t += self.frame_time_ms
 
+    def add_lines(self, lines):
+        """Lines already formatted for this frame's time stamp (``spike_file_lines_all_streams`` with ``self.t``)."""
+        self.lines += lines
+        self.t += self.frame_time_ms
+
     def getvalue(self):
         return "\n".join(self.lines)
 
@@ -87,3 +92,26 @@ def emit_spikes(sender, lists, time_per_spike_pack_ms, label, clock=None, sleep=
                 sleep(max_time_s - elapsed)
             sent += 1
     return sent
+
+
+def spike_file_lines_all_streams(result, flag_shift, data_shift, data_mask, t_frame_ms, t_bin_ms):
+    """``spike_file_lines`` for every stream of a ``StepResult`` at once: one key kernel launch and two device-to-host
+    copies (keys, CSR row pointers) for the whole batch instead of one round trip per stream.  Returns a list with one
+    list of lines per stream."""
+    owner = result._owner
+    if owner.cfg.uncoded and owner.cfg.output_type in (OUTPUT_RATE, OUTPUT_TIME):
+        raise ValueError("spike files hold 16-bit keys; the uncoded rate/time encoders emit (row, col, p) triples")
+    off = np.asarray(result.offsets_host(), dtype=np.int64)
+    keys = result.keys(flag_shift, data_shift, data_mask).cpu().numpy()
+    n_slots, S = owner.n_slots, owner.S
+    per = 2 * n_slots
+    # events are ordered stream -> slot -> (pos, neg): the slot of event e is the segment it falls in, halved
+    seg_len = np.diff(off)
+    slot_of_seg = (np.arange(S * per) % per) // 2
+    times = float(t_frame_ms) + np.repeat(slot_of_seg, seg_len).astype(np.float64) * float(t_bin_ms)
+    bounds = off[::per] if per else np.zeros(S + 1, dtype=np.int64)
+    out = []
+    for s in range(S):
+        lo, hi = int(bounds[s]), int(bounds[s + 1])
+        out.append(["%s %f" % (int(k), t) for k, t in zip(keys[lo:hi].tolist(), times[lo:hi].tolist())])
+    return out
