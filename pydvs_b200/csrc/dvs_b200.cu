@@ -325,6 +325,49 @@ __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ ExpandAr
         return;
       }
     }
+    // Tasks that fit a group of G = 8 (then 16) lanes: 32 / G tasks are expanded per pass (group g walks the tasks
+    // owned by its own lanes), the ballot of a slot is cut into the groups' bit fields.
+    auto grouped = [&](const int G, const int n_lo, const int n_hi) {
+      const int g0 = lane & ~(G - 1), sub = lane & (G - 1);
+      const unsigned sub_lt = (1u << sub) - 1u, gm = G == 8 ? 0xffu : 0xffffu;
+#pragma unroll 1
+      for (int k = 0; k < G; ++k) {
+        const int src_g = g0 + k;
+        const int n_g = __shfl_sync(kFull, my_n, src_g);
+        const bool act = n_g > n_lo && n_g <= n_hi;  // uniform within the group
+        if (!__any_sync(kFull, act)) continue;
+        const dvs_record *rec_g = reinterpret_cast<const dvs_record *>(__shfl_sync(kFull, (unsigned long long)my_rec, src_g));
+        const int pol_g = __shfl_sync(kFull, my_pol, src_g);
+        uint2 r = make_uint2(0u, 0u);
+        int desc = (A.enc.mode == DVS_ENC_TIME) ? -1 : 0;
+        if (act && sub < n_g) {
+          r = *reinterpret_cast<const uint2 *>(rec_g + sub);
+          desc = (r.y >> 16) ? (int)(r.y >> 16) - 2 : enc_desc(A.enc, (int)(short)(r.y & 0xffff), pol_g == 0, status);
+        }
+        const uint32_t xy = (r.x >> 16) | (r.x << 16);
+        const uint32_t pb = (pol_g ? 0xffffu : 1u) << 16;
+        const int dmax = __reduce_max_sync(kFull, desc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (A.enc.mode == DVS_ENC_RATE ? j >= dmax : j > dmax) break;
+          const uint32_t bj = __shfl_sync(kFull, my_base[j], src_g);
+          const bool m = (A.enc.mode == DVS_ENC_RATE) ? desc > j : desc == j;
+          const unsigned gb = (__ballot_sync(kFull, m) >> g0) & gm;
+          if (m) *reinterpret_cast<uint2 *>(ev_s + bj + __popc(gb & sub_lt)) = make_uint2(xy, (uint32_t)j | pb);
+        }
+      }
+    };
+    constexpr int kGroupTask = 16;
+    if (__any_sync(kFull, my_n > kSmallTask && my_n <= 8)) grouped(8, kSmallTask, 8);
+    if (__any_sync(kFull, my_n > 8 && my_n <= kGroupTask)) grouped(16, 8, kGroupTask);
+    if (__any_sync(kFull, my_n > kSmallTask && my_n <= kGroupTask)) {
+      todo = __ballot_sync(kFull, my_n > kGroupTask);
+      if (todo == 0) {
+        status = __reduce_or_sync(kFull, status);
+        if (status && lane == 0 && A.status) atomicOr(A.status, (int)status);
+        return;
+      }
+    }
     int src = __ffs(todo) - 1;
     todo &= todo - 1;
     const dvs_record *rec = reinterpret_cast<const dvs_record *>(__shfl_sync(kFull, (unsigned long long)my_rec, src));
