@@ -240,13 +240,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   }
   __syncthreads();
   const uint32_t ent = lane < J * NW ? wtot[lane] : 0u;  // every warp scans the <= 32 totals redundantly
-  uint32_t ent_in = ent;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t y = __shfl_up_sync(kFull, ent_in, o);
-    if (lane >= o) ent_in += y;
-  }
-  const int n_cand = (int)__shfl_sync(kFull, ent_in, 31);
+  const int n_cand = (int)__reduce_add_sync(kFull, ent);  // redux.sync: the tile's candidate count
   const bool unsafe = __any_sync(kFull, lane < NW && wtot[96 + lane] != 0);
   if (n_cand == 0 && !unsafe) {  // quiet tile: no records, no events, reference untouched (unless it decays)
     if (ADAPT) store_thresholds();
@@ -263,7 +257,6 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   if (decay) store_decayed_reference();
   {
     // entry: tile-local pixel index (13 bits) | reference << 13 (8 bits) | abs_diff << 21 (8 bits) | negative << 29
-    const uint32_t ent_ex = ent_in - ent;
     const uint32_t ex_lo = in_lo - cnt_lo, ex_hi = in_hi - cnt_hi;
     auto entry_of = [&](int q, int c, int r) -> uint32_t {
       // the entry carries the reference the update starts from: trunc(history_weight * r)
@@ -273,7 +266,8 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     uint32_t pos_of[J];
 #pragma unroll
     for (int j = 0; j < J; ++j)
-      pos_of[j] = __shfl_sync(kFull, ent_ex, j * NW + warp) + (((j < 2 ? ex_lo : ex_hi) >> (16 * (j & 1))) & 0xffffu);
+      pos_of[j] = __reduce_add_sync(kFull, lane < j * NW + warp ? ent : 0u) +  // candidates of earlier (group, warp) pairs
+                  (((j < 2 ? ex_lo : ex_hi) >> (16 * (j & 1))) & 0xffffu);
     if (PAIR) {
       // after the 2x2 inhibition an area (word w of the upper and of the lower row group) holds at most one
       // candidate: walk the four areas of a column block once, instead of the set bits of each row group
