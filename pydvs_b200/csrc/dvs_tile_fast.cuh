@@ -367,15 +367,9 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   __syncthreads();
   uint32_t base = 0, totals = 0;
   {
-    const uint32_t t = lane < NW ? wtot[64 + lane] : 0u;
-    uint32_t t_in = t;
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {  // NW <= 8
-      const uint32_t y = __shfl_up_sync(kFull, t_in, o);
-      if (lane >= o) t_in += y;
-    }
-    base = __shfl_sync(kFull, t_in - t, warp);
-    totals = __shfl_sync(kFull, t_in, 7);
+    const uint32_t t = lane < NW ? wtot[64 + lane] : 0u;  // pos | neg << 16 per warp: the packed sums cannot carry
+    base = __reduce_add_sync(kFull, lane < warp ? t : 0u);
+    totals = __reduce_add_sync(kFull, t);
   }
   const int n_pos_tile = totals & 0xffff, n_neg_tile = totals >> 16;
 
