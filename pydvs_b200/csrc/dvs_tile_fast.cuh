@@ -233,15 +233,15 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     }
   }
   if (lane == 31) {
-    wtot[0 * NW + warp] = in_lo & 0xffff;
+    wtot[0 * NW + warp] = (in_lo & 0xffff) | (w_unsafe ? 0x80000000u : 0u);  // bit 31: a pixel outside [0, 255]
     if (J > 1) wtot[1 * NW + warp] = in_lo >> 16;
     if (J > 2) { wtot[2 * NW + warp] = in_hi & 0xffff; wtot[3 * NW + warp] = in_hi >> 16; }
-    wtot[96 + warp] = w_unsafe ? 1u : 0u;
   }
   __syncthreads();
-  const uint32_t ent = lane < J * NW ? wtot[lane] : 0u;  // every warp scans the <= 32 totals redundantly
+  const uint32_t ent_raw = lane < J * NW ? wtot[lane] : 0u;  // every warp reads the <= 32 totals
+  const bool unsafe = __any_sync(kFull, (ent_raw >> 31) != 0u);
+  const uint32_t ent = ent_raw & 0x7fffffffu;
   const int n_cand = (int)__reduce_add_sync(kFull, ent);  // redux.sync: the tile's candidate count
-  const bool unsafe = __any_sync(kFull, lane < NW && wtot[96 + lane] != 0);
   if (n_cand == 0 && !unsafe) {  // quiet tile: no records, no events, reference untouched (unless it decays)
     if (ADAPT) store_thresholds();
     if (decay) store_decayed_reference();
