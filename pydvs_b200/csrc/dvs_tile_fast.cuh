@@ -314,7 +314,10 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   __syncthreads();
 
   // ---- 4a. one candidate per lane: reference update, list membership, histogram, staged record ------
-  const int per_warp = (((n_cand + NW - 1) / NW) + 31) & ~31;
+  // 32-candidate chunks per warp = ceil(ceil(n_cand / 32) / NW), without an integer division by the run-time NW
+  int chunks_per_warp = 1;
+  while (chunks_per_warp * NW < ((n_cand + 31) >> 5)) ++chunks_per_warp;
+  const int per_warp = chunks_per_warp << 5;
   const int lo = min(n_cand, warp * per_warp), hi = min(n_cand, lo + per_warp);
   const unsigned magic = A.upd.div_thr.magic;
   const int max_n = A.upd.max_time_ms;
