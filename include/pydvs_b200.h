@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DVS_ABI_VERSION 1
+#define DVS_ABI_VERSION 2
 
 /* error codes (>= 1000 so they cannot collide with cudaError_t) */
 #define DVS_OK 0
@@ -135,6 +135,10 @@ typedef struct dvs_step_params {
                              * staged form (bulk async copies + mbarrier) whenever the tile shape allows it   */
   int32_t drop_silent;      /* 1: records that emit no event (coded rate, k == 0) may be left out of the
                              * tile lists: identical events, but the lists no longer are split_spikes' output */
+  int32_t record_stride;    /* records reserved per tile region; 0 = tile_rows * W.  With k x k inhibition a tile
+                             * holds at most (tile_rows / k) * (W / k) records, so callers may pass that bound
+                             * (the same number is the `tile_px` argument of dvs_aer_expand / dvs_gather_split) */
+  int32_t reserved0;
   double history_weight;
   dvs_enc_params enc;
   const void *curr;         /* [S][H][W] frames, int16 or uint8                               */
@@ -143,7 +147,7 @@ typedef struct dvs_step_params {
   int16_t *diff_out;        /* optional planes (NULL = skip): what thresholded_difference and */
   int16_t *abs_diff_out;    /*   local_inhibition would have returned for this frame          */
   int16_t *spikes_out;
-  dvs_record *records;      /* S * tiles_per_stream * tile_rows * W records (tile-local lists) */
+  dvs_record *records;      /* S * tiles_per_stream * record_stride records (tile-local lists)  */
   uint32_t *tile_counts;    /* [S][C][tiles_per_stream]                                       */
   int32_t *status;          /* device status word or NULL                                     */
   int32_t *redo;            /* optional scratch, 1 + S * tiles_per_stream int32: enables the    */

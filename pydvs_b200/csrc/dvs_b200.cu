@@ -872,6 +872,7 @@ static int fill_tiling(TileArgs &A, const dvs_tiling &t, int n_slots_or_none, in
   A.S = t.S; A.H = t.H; A.W = t.W; A.tile_rows = t.tile_rows;
   A.tiles_per_stream = (t.H + t.tile_rows - 1) / t.tile_rows;
   A.tile_px = t.tile_rows * t.W;
+  A.rec_stride = A.tile_px;
   A.inv_w = t.W >= 2 ? (unsigned)((0x100000000ull + (unsigned)t.W - 1) / (unsigned)t.W) : 0u;
   A.C = 2 + 2 * (enc_mode == DVS_ENC_NONE ? 0 : n_slots_or_none);
   return DVS_OK;
@@ -895,6 +896,12 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
   if (k > 1 && (A.W % k || A.H % k || A.tile_rows % k))
     return fail(DVS_ERR_INVALID_ARGUMENT, "inhibition needs W, H and tile_rows divisible by inh_k (reference: IndexError)");
   A.adaptive = p->adaptive; A.polarity = p->polarity; A.uncoded = p->uncoded; A.inh_k = k;
+  if (p->record_stride != 0) {  // the caller sized the tile regions by the inhibition bound: one record per k x k area
+    const int bound = k > 1 ? (A.tile_rows / k) * (A.W / k) : A.tile_px;
+    if (p->record_stride < bound || p->record_stride > A.tile_px)
+      return fail(DVS_ERR_INVALID_ARGUMENT, "record_stride below the per-tile record bound (or above tile_rows * W)");
+    A.rec_stride = p->record_stride;
+  }
   A.thr_scalar = p->threshold;
   A.upd.mode = p->update_mode; A.upd.uncoded = p->uncoded; A.upd.threshold = p->threshold;
   A.upd.min_thr = p->min_thr; A.upd.max_thr = p->max_thr; A.upd.thr_down = p->thr_down; A.upd.thr_up = p->thr_up;

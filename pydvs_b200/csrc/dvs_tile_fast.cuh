@@ -183,7 +183,14 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
         uint32_t t_dn, t_up = 0;
         if (!A.upd.uncoded) {
           t_dn = __vminu2(__vmaxu2(th, mnd2) - dn2, mx2);                // clip(th - down, min, max)
-          if (flags8[j]) t_up = __vminu2(__vmaxu2(th + up2, mn2), mx2);  // clip(th + up, min, max)
+          if (flags8[j]) {
+            // clip(th + up, min, max) on int16 lanes: a sum above 32767 wraps negative in the reference (gs:292)
+            // and therefore clips to min
+            const uint32_t su = th + up2;  // th, up <= 32767: no carry between the lanes
+            t_up = __vminu2(__vmaxu2(su, mn2), mx2);
+            const uint32_t wrapped = ((su & 0x80008000u) >> 15) * 0xffffu;
+            t_up = (t_up & ~wrapped) | (mn2 & wrapped);
+          }
         } else {
           // uncoded twin gsu:286-295: += up only while th < max, -= down only while th > min, no clip.
           // lane-wise compare of values < 2^15: bit 15 of ((x | 0x8000) - y) is set iff x >= y
@@ -335,7 +342,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       const bool neg = (e >> 29) & 1u;
       const int y = (int)__umulhi((unsigned)q, A.inv_w), x = q - y * A.W;
       int upd;
-      if (ADAPT) upd = np_floordiv(a, (int)wl_thr[i]) * A.upd.min_thr;       // gs:287-289: (a // thr) * min_threshold
+      if (ADAPT) upd = np_floordiv(a, (int)wl_thr[i]);                       // gs:287-289: (a // thr) [* min_threshold below]
       else if (SIMPLE || A.upd.mode == DVS_UPD_RATE) upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;  // gs:244-249
       else {  // time-binary updates gs:374-376 / gs:421-423: log2 table of abs_diff (raw) or of abs_diff // T
         const int idx = A.upd.mode == DVS_UPD_TIME_BIN_THR ? (int)__umulhi((unsigned)a, magic) : a;
@@ -343,7 +350,10 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
         if (idx >= A.upd.lut_len) status |= DVS_STATUS_LUT_INDEX;
         else upd = (int)__ldg(A.upd.lut + idx) * (A.upd.mode == DVS_UPD_TIME_BIN_THR ? T : 1);
       }
-      ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
+      if (ADAPT) {  // gs:289: int16 products and sums wrap before the clip (thresholds below min_threshold can get there)
+        const int u = w16((neg ? -upd : upd) * A.upd.min_thr);
+        ref_t[q] = (int16_t)clip(w16(r + u), 0, 255);
+      } else ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
       int desc = 0;
       if (SIMPLE) {
         tp = !neg; tn = neg;
@@ -378,9 +388,9 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
 
   // ---- 4b. coalesced copy of the warp's staged records to their ranks in the tile's lists ----------
   if (w_pos | w_neg) {
-    const size_t region = (size_t)tile * A.tile_px;
+    const size_t region = (size_t)tile * A.rec_stride;
     dvs_record *pos_dst = A.records + region + (base & 0xffff);
-    dvs_record *neg_dst = A.records + region + (A.tile_px - n_neg_tile) + (base >> 16);
+    dvs_record *neg_dst = A.records + region + (A.rec_stride - n_neg_tile) + (base >> 16);
     for (int i = lane; i < (int)w_pos; i += 32) *reinterpret_cast<uint2 *>(pos_dst + i) = rec_sm[lo + i];
     for (int i = lane; i < (int)w_neg; i += 32) *reinterpret_cast<uint2 *>(neg_dst + i) = rec_sm[hi - 1 - i];
   }

@@ -15,6 +15,7 @@ enum { INH_NONE = 0, INH_K2 = 2, INH_GENERIC = -1 };
 
 struct TileArgs {
   int S, H, W, tile_rows, tiles_per_stream, tile_px, C;
+  int rec_stride;          // records reserved per tile region (tile_px, or the inhibition bound tile_px / k^2)
   int adaptive, polarity, uncoded, inh_k, vec_ok, fast_hist, drop_silent, use_staged;
   int thr_scalar;
   unsigned inv_w;          // ceil(2^32 / W): q / W == umulhi(q, inv_w) for q < 32768
@@ -213,9 +214,9 @@ DEV void tile_compact(const TileArgs &A, int tile, int s_idx, int t_idx, int row
   unsigned long long hp = 0, hn = 0;  // 8 x 8-bit register histograms (fast_hist)
 
   if (totals != 0) {
-    const size_t region = (size_t)tile * A.tile_px;
+    const size_t region = (size_t)tile * A.rec_stride;
     dvs_record *pos_dst = A.records + region;
-    dvs_record *neg_dst = A.records + region + (A.tile_px - n_neg_tile);
+    dvs_record *neg_dst = A.records + region + (A.rec_stride - n_neg_tile);
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       if ((posm[j] | negm[j]) == 0) continue;

@@ -96,6 +96,10 @@ class StepResult:
     ``events[seg_offsets[(s * n_slots + slot) * 2 + pol] : seg_offsets[... + 1]]`` are the events of
     stream ``s``, time slot ``slot``, list ``pol`` (0 = pos, 1 = neg) in the reference's order
     (SURVEY.md Appendix A.7).  Each event is 8 bytes: uint16 x, y, t and int16 p.
+
+    Lifetime: the result ALIASES the stream object's step buffers (no copy) and fetches the row pointers lazily,
+    so it describes its step only until the next ``step()`` on the same object (``pipeline_depth`` steps when
+    pipelined).  Copy ``events()`` / ``offsets_host()`` first if an older step must outlive a newer one.
     """
 
     def __init__(self, owner, events, seg_offsets, status, ready=None):
@@ -162,9 +166,13 @@ class StepResult:
 
 
 class DVSStreams:
+    # below this many pixels per step (all streams) a step is launch-bound and is replayed as a CUDA graph
+    AUTO_GRAPH_MAX_PX = 1 << 26
+    GRAPH_CACHE = 16          # distinct frame buffers (by address) that get their own captured graph
+
     def __init__(self, cfg: DVSConfig, device=None, event_capacity: Optional[int] = None,
                  debug_planes: bool = False, force_generic: bool = False, pipeline_depth: int = 1,
-                 split_lists: bool = True):
+                 split_lists: bool = True, graph="auto"):
         if not torch.cuda.is_available():
             raise RuntimeError("pydvs_b200 needs a CUDA device (there is no CPU path)")
         self.cfg = cfg = cfg.resolved()
@@ -187,6 +195,8 @@ class DVSStreams:
         self.tile_rows = tr
         self.tps = (self.H + tr - 1) // tr
         self.tile_px = tr * self.W
+        # records reserved per tile: with k x k inhibition at most one record per area (tile_px / k^2)
+        self.rec_stride = (tr // k) * (self.W // k) if k > 1 else self.tile_px
         self.C = 2 + 2 * self.n_slots
         dev = self.device
         # state
@@ -209,13 +219,16 @@ class DVSStreams:
         # step n runs on a side stream while the tile pass of step n+1 already runs on the caller's stream.
         n_tiles = self.S * self.tps
         if event_capacity is None:
-            event_capacity = max(1024, (self.S * self.P) // 2)
+            # capacity policy: one event per eight pixels (1 B/px of HBM); a step that overflows sets a status bit,
+            # check_status() raises OverflowError and grow_events() re-expands the kept records (reserve_events()
+            # sizes the buffer up front when the caller knows the event volume)
+            event_capacity = max(1 << 16, (self.S * self.P) // 8)
         self.event_capacity = int(event_capacity)
         self.pipeline_depth = max(1, int(pipeline_depth))
 
         def make_set():
             counts = torch.zeros(self.S * self.C * self.tps, dtype=torch.int32, device=dev)
-            return {"records": torch.empty(n_tiles * self.tile_px, dtype=torch.int64, device=dev),
+            return {"records": torch.empty(n_tiles * self.rec_stride, dtype=torch.int64, device=dev),
                     "tile_counts": counts, "tile_excl": torch.zeros_like(counts),
                     "stream_totals": torch.zeros(self.S * self.C, dtype=torch.int32, device=dev),
                     "seg_offsets": torch.zeros(self.S * self.n_slots * 2 + 1, dtype=torch.int64, device=dev),
@@ -237,6 +250,12 @@ class DVSStreams:
         self._enc = self._make_enc()
         self._params = self._make_params()
         self.frames_done = 0
+        # CUDA-graph replay of launch-bound steps: "auto" = small problems only, True = always, False = never
+        if graph == "auto":
+            graph = self.S * self.P <= self.AUTO_GRAPH_MAX_PX
+        self.use_graph = bool(graph) and self.pipeline_depth == 1
+        self._graphs = {}          # frame buffer address -> captured step
+        self._graph_misses = 0
 
     # the buffer set of the most recent step
     records = property(lambda self: self._sets[self._cur]["records"])
@@ -266,6 +285,7 @@ class DVSStreams:
         p.inh_k, p.polarity, p.history_weight = self.inh_k, int(cfg.polarity), float(cfg.history_weight)
         p.force_generic = int(self.force_generic)
         p.drop_silent = int(not self.split_lists)
+        p.record_stride = self.rec_stride
         p.enc = self._enc
         p.ref = self.ref.data_ptr()
         p.thr = self.thr.data_ptr() if self.thr is not None else None
@@ -283,11 +303,46 @@ class DVSStreams:
             raise ValueError("frames must be a CUDA tensor of dtype %s" % want)
         if frames.numel() != self.S * self.P or not frames.is_contiguous():
             raise ValueError("frames must be contiguous with shape [%d, %d, %d]" % (self.S, self.H, self.W))
+        if self.use_graph and expand and self.frames_done > 0:   # the first step runs eagerly (module load, attributes)
+            g = self._graphs.get(frames.data_ptr())
+            if g is None and len(self._graphs) < self.GRAPH_CACHE:
+                g = self._capture_step(frames)
+            if g is not None:
+                self._cur = 0
+                self.frames_done += 1
+                g[0].replay()
+                return StepResult(self, self.events, self.seg_offsets, self.status)
+            self._graph_misses += 1
+            if self._graph_misses > 4 * self.GRAPH_CACHE:   # the caller hands a fresh buffer every frame: stop trying
+                self.use_graph = False
         self.begin_step()
         self.tile_pass(frames)
         self.scan()
         ready = self.expand_async() if expand else None
         return StepResult(self, self.events, self.seg_offsets, self.status, ready)
+
+    def _capture_step(self, frames):
+        """Record the launches of one step reading the buffer at ``frames.data_ptr()`` into a CUDA graph.  The graph is
+        only replayed for a validated frames tensor at that same address, so no reference to ``frames`` is kept."""
+        graph = torch.cuda.CUDAGraph()
+        self._cur = 0
+        with torch.cuda.graph(graph):
+            self.tile_pass(frames)
+            self.scan()
+            self.expand()
+        entry = (graph,)
+        self._graphs[frames.data_ptr()] = entry
+        return entry
+
+    def reserve_events(self, capacity):
+        """Make room for ``capacity`` events per step (re-allocates; drops captured graphs)."""
+        if int(capacity) <= self.event_capacity:
+            return
+        self.drain()
+        self.event_capacity = int(capacity)
+        for st in self._sets:
+            st["events"] = torch.empty(self.event_capacity, dtype=torch.int64, device=self.device)
+        self._graphs.clear()
 
     # the launches of a step, individually (bench.py times K1 on its own)
     def begin_step(self):
@@ -336,23 +391,32 @@ class DVSStreams:
         launches from Python (128x128 / 640x480 single streams are launch-bound)."""
         if self.pipeline_depth != 1:
             raise ValueError("graph capture uses the single-buffered pipeline (pipeline_depth=1)")
-        self.step(frames)          # warm-up outside the capture: function attributes, lazy module load
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            self.tile_pass(frames)
-            self.scan()
-            self.expand()
-        self._graph, self._graph_frames = graph, frames
-        return graph
+        if self.frames_done == 0:
+            # warm-up outside the capture (function attributes, lazy module load) on a snapshot of the state, so
+            # that capturing leaves ref / thr / frames_done exactly as they were: replaying the first frame
+            # afterwards applies it once, not twice
+            keep = (self.ref.clone(), None if self.thr is None else self.thr.clone())
+            use_graph, self.use_graph = self.use_graph, False
+            self.step(frames)
+            self.use_graph = use_graph
+            torch.cuda.synchronize()
+            self.ref.copy_(keep[0])
+            if self.thr is not None:
+                self.thr.copy_(keep[1])
+            self.status.zero_()
+            self.frames_done = 0
+        self._graph, self._graph_frames = self._capture_step(frames)[0], frames
+        return self._graph
 
     def replay(self) -> StepResult:
+        """Replay the step captured by :meth:`capture` (the result aliases the step buffers: valid until the next step)."""
+        self._cur = 0
         self._graph.replay()
         self.frames_done += 1
         return StepResult(self, self.events, self.seg_offsets, self.status)
 
     def expand(self):
-        check(lib.dvs_aer_expand(self.S, self.tps, self.tile_px, C.byref(self._enc), _ptr(self.records),
+        check(lib.dvs_aer_expand(self.S, self.tps, self.rec_stride, C.byref(self._enc), _ptr(self.records),
                                  _ptr(self.tile_counts), _ptr(self.tile_excl), _ptr(self.seg_offsets),
                                  _ptr(self.events), self.event_capacity, _ptr(self.status), current_stream_ptr()))
 
@@ -362,6 +426,7 @@ class DVSStreams:
         self.event_capacity = int(capacity)
         for st in self._sets:
             st["events"] = torch.empty(self.event_capacity, dtype=torch.int64, device=self.device)
+        self._graphs.clear()   # captured steps point at the old buffer
         self.status.zero_()
         self.expand()
         return StepResult(self, self.events, self.seg_offsets, self.status)
@@ -388,7 +453,7 @@ class DVSStreams:
         n_pos, n_neg = int(tot[0]), int(tot[1])
         pos = torch.empty((3, n_pos), dtype=torch.int16, device=self.device)
         neg = torch.empty((3, n_neg), dtype=torch.int16, device=self.device)
-        check(lib.dvs_gather_split(stream, self.tps, self.tile_px, self.n_slots, _ptr(self.records),
+        check(lib.dvs_gather_split(stream, self.tps, self.rec_stride, self.n_slots, _ptr(self.records),
                                    _ptr(self.tile_counts), _ptr(self.tile_excl), _ptr(pos), max(n_pos, 1),
                                    _ptr(neg), max(n_neg, 1), current_stream_ptr()))
         return neg, pos

@@ -46,3 +46,39 @@ def saccade_frames(images, t, offsets, device="cuda", bg=0, dtype=torch.int16):
     gathered = torch.gather(images.reshape(S, H * W).to(device), 1, idx.reshape(S, H * W)).reshape(S, H, W)
     out = torch.where(ok, gathered, out)
     return out.to(dtype).contiguous()
+
+
+# ---- counter-based frames: the same pixels from torch (any device) and from NumPy (bench.py's reference arm) ----
+_M32 = 0xFFFFFFFF
+
+
+def _mix32(h):
+    """lowbias32-style integer hash on int64 tensors holding 32-bit values (constants < 2**31, so no
+    product leaves the int64 range: NumPy and torch agree bit for bit on every device)."""
+    h = h ^ (h >> 16)
+    h = (h * 0x7FEB352D) & _M32
+    h = h ^ (h >> 15)
+    h = (h * 0x2C1B3C6D) & _M32
+    return h ^ (h >> 16)
+
+
+def hashed_frames(S, H, W, t, pattern="bar", device="cuda", stream_offset=0, noise=8, bg=64, bar=200,
+                  dtype=torch.int16):
+    """Frame ``t`` of streams ``stream_offset .. stream_offset + S - 1``.
+
+    ``bar``: the moving bar of :func:`moving_bar` plus uniform noise in ``[-noise, noise]`` drawn from a
+    hash of (global stream id, t, pixel index); ``dense``: uniform pixels in [0, 255] from the same hash.
+    ``bench.np_hashed_frame`` is the NumPy twin (checked in tests/test_abi_and_host.py)."""
+    P = H * W
+    q = torch.arange(P, device=device, dtype=torch.int64).view(1, P)
+    sid = (torch.arange(S, device=device, dtype=torch.int64) + stream_offset).view(S, 1)
+    h = _mix32((((sid * 1000003 + t) * 2654435761) + q * 40503) & _M32)
+    if pattern == "dense":
+        return (h & 0xFF).view(S, H, W).to(dtype).contiguous()
+    bw, sp = max(1, W // 16), max(1, W // 64)
+    x = q % W
+    x0 = ((sid * 37) % W + t * sp) % W
+    base = torch.where(((x - x0) % W) < bw, bar, bg)
+    if noise:
+        base = base + (h % (2 * noise + 1)) - noise
+    return base.clamp_(0, 255).view(S, H, W).to(dtype).contiguous()

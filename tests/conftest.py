@@ -15,8 +15,7 @@ def pytest_configure(config):
     spec = importlib.util.spec_from_file_location("_pydvs_build", os.path.join(ROOT, "pydvs_b200", "build.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    if not os.path.exists(mod.LIB):
-        mod.build()
+    mod.ensure_built()   # digest check: also rebuilds a library that is stale relative to csrc/
 
 
 def _has_gpu():

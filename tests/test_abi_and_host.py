@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), "libpydvs_b200.so does not export %s" % n
     assert set(_lib.EXPORTS) == set(names), "ctypes binding and header disagree"
-    assert _lib.lib.dvs_abi_version() == 1
+    assert _lib.lib.dvs_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_the_header():
@@ -34,7 +34,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.EncParams) == 32
     assert ctypes.sizeof(_lib.Tiling) == 16
     assert _lib.StepParams.history_weight.offset % 8 == 0
-    assert ctypes.sizeof(_lib.StepParams) == 16 + 14 * 4 + 8 + 32 + 10 * 8
+    assert ctypes.sizeof(_lib.StepParams) == 16 + 16 * 4 + 8 + 32 + 10 * 8
 
 
 def test_header_is_plain_c_and_links_against_the_library(tmp_path):

@@ -18,7 +18,7 @@ def _key_params(W, H):
 def _run_case(S, H, W, *, output_type="RATE", frames=6, source="random", inh=0, adaptive=False, hw=1.0,
               polarity=2, uncoded=False, frame_dtype="int16", threshold=12, max_time_ms=8, num_bins=None,
               thr0=None, tile_rows=None, seed=0, lut_bits=(2, 6), ref0=128, debug=True, force_generic=False,
-              split_lists=True):
+              split_lists=True, cfg_extra=None):
     from oracle import oracle as orc
     from pydvs_b200 import DVSConfig, DVSStreams, synth
     import pydvs_b200.generate_spikes as gs
@@ -27,7 +27,7 @@ def _run_case(S, H, W, *, output_type="RATE", frames=6, source="random", inh=0, 
     cfg = DVSConfig(width=W, height=H, streams=S, output_type=output_type, polarity=polarity, threshold=threshold,
                     adaptive_threshold=adaptive, history_weight=hw, max_time_ms=max_time_ms, num_bins=num_bins,
                     inh_area_width=inh, uncoded=uncoded, frame_dtype=frame_dtype, log2_table=lut,
-                    threshold0=thr0, tile_rows=tile_rows, ref0=ref0)
+                    threshold0=thr0, tile_rows=tile_rows, ref0=ref0, **(cfg_extra or {}))
     dvs = DVSStreams(cfg, debug_planes=debug, event_capacity=S * H * W * max(8, max_time_ms),
                      force_generic=force_generic, split_lists=split_lists)
     rc = dvs.cfg
@@ -298,6 +298,18 @@ def test_fast_adaptive_kernel_declines_out_of_range_tiles():
     _run_case(1, 8, 1920, output_type="RATE", adaptive=True, inh=2, source="wide", frames=3, thr0=12, debug=False)
 
 
+def test_fast_adaptive_kernel_int16_wrap_boundaries():
+    # gs:289-297 in int16: th + up above 32767 wraps negative and clips to min (not max); (a // th) * min_threshold wraps
+    # for a caller-supplied plane below min_threshold.  Fast kernel and generic body must both follow the oracle.
+    for fg in (False, True):
+        _run_case(2, 16, 64, output_type="RATE", adaptive=True, frames=4, thr0=100, debug=False, force_generic=fg,
+                  cfg_extra=dict(threshold_delta_up=32700, max_threshold=32767))
+        _run_case(2, 16, 64, output_type="RATE", adaptive=True, frames=4, thr0=1, debug=False, force_generic=fg,
+                  cfg_extra=dict(min_threshold=150, max_threshold=400))
+        _run_case(2, 8, 1920, output_type="RATE", adaptive=True, inh=2, frames=3, thr0=1, debug=False, force_generic=fg,
+                  cfg_extra=dict(min_threshold=150, max_threshold=32767, threshold_delta_up=32700))
+
+
 def test_pipelined_expand_matches_in_line_expand():
     """pipeline_depth 2: the expand of step n runs on a side stream, double-buffered against step n+1."""
     from pydvs_b200 import DVSConfig, DVSStreams, synth
@@ -320,18 +332,45 @@ def test_pipelined_expand_matches_in_line_expand():
 def test_cuda_graph_replay_matches_eager_steps():
     from pydvs_b200 import DVSConfig, DVSStreams, synth
     cfg = DVSConfig(width=128, height=128, streams=1, output_type="RATE", inh_area_width=2)
-    eager, graphed = DVSStreams(cfg), DVSStreams(cfg)
+    eager, graphed = DVSStreams(cfg, graph=False), DVSStreams(cfg, graph=False)
     static = synth.moving_bar(1, 128, 128, 0, noise=6, seed=1)
-    eager.step(static)
-    graphed.capture(static)            # performs step 0 as its warm-up ...
-    graphed.ref.copy_(eager.ref)       # ... and the capture pass itself launches nothing
-    for t in range(1, 8):
+    graphed.capture(static)            # warms up on a snapshot: state and frame counter are left untouched
+    assert graphed.frames_done == 0 and int((graphed.ref != 128).sum()) == 0
+    for t in range(0, 8):
         f = synth.moving_bar(1, 128, 128, t, noise=6, seed=1)
         re = eager.step(f)
         static.copy_(f)
         rg = graphed.replay()
         assert torch.equal(eager.ref, graphed.ref)
         assert torch.equal(re.seg_offsets, rg.seg_offsets) and torch.equal(re.events(), rg.events())
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_automatic_graph_replay_of_small_steps(adaptive):
+    # launch-bound shapes are replayed as CUDA graphs keyed by the frame buffer's address (DVSStreams.step):
+    # a ring of frame buffers, a buffer rewritten in place and fresh tensors must all match the eager object
+    from pydvs_b200 import DVSConfig, DVSStreams, synth
+    cfg = DVSConfig(width=96, height=54, streams=5, output_type="TIME" if adaptive else "RATE", max_time_ms=4,
+                    adaptive_threshold=adaptive, threshold0=12 if adaptive else None, inh_area_width=0 if adaptive else 2)
+    eager, auto = DVSStreams(cfg, graph=False), DVSStreams(cfg)
+    assert auto.use_graph and not eager.use_graph
+    ring = [synth.moving_bar(5, 54, 96, t, noise=6, seed=2) for t in range(3)]
+    static = torch.empty_like(ring[0])
+    for t in range(12):
+        if t < 6:
+            f = ring[t % 3]
+        elif t < 9:
+            static.copy_(synth.moving_bar(5, 54, 96, t, noise=6, seed=2))
+            f = static
+        else:
+            f = synth.moving_bar(5, 54, 96, t, noise=6, seed=2)
+        re, ra = eager.step(f), auto.step(f)
+        assert torch.equal(eager.ref, auto.ref)
+        if adaptive:
+            assert torch.equal(eager.thr, auto.thr)
+        assert torch.equal(re.seg_offsets, ra.seg_offsets) and torch.equal(re.events(), ra.events())
+    assert len(auto._graphs) >= 4
+    auto.check_status()
 
 
 def test_event_overflow_is_recoverable():
