@@ -219,10 +219,11 @@ class DVSStreams:
         # step n runs on a side stream while the tile pass of step n+1 already runs on the caller's stream.
         n_tiles = self.S * self.tps
         if event_capacity is None:
-            # capacity policy: one event per eight pixels (1 B/px of HBM); a step that overflows sets a status bit,
-            # check_status() raises OverflowError and grow_events() re-expands the kept records (reserve_events()
-            # sizes the buffer up front when the caller knows the event volume)
-            event_capacity = max(1 << 16, (self.S * self.P) // 8)
+            # capacity policy: one event per two pixels (4 B/px of HBM) covers the dense start-up frame of the
+            # reference's defaults; a step that overflows sets a status bit, check_status() raises OverflowError and
+            # grow_events() re-expands the kept records.  Callers that know their event volume pass a small
+            # event_capacity and size it with reserve_events() (bench.py: measured steady state x 1.5)
+            event_capacity = max(1024, (self.S * self.P) // 2)
         self.event_capacity = int(event_capacity)
         self.pipeline_depth = max(1, int(pipeline_depth))
 

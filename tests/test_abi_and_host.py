@@ -198,3 +198,50 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "dvs_oracle" not in text, f
+
+
+def test_bench_frame_generators_agree_and_the_reference_arm_never_loads_the_product():
+    """bench.py's NumPy frame generator (reference arm) and pydvs_b200.synth.hashed_frames (GPU arm) produce the same
+    pixels; the reference arm runs without importing pydvs_b200 (so it cannot map libpydvs_b200.so)."""
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    from pydvs_b200 import synth
+    for pat in ("bar", "dense"):
+        for (S, H, W, t, off) in [(3, 16, 64, 5, 7), (2, 54, 96, 0, 250)]:
+            a = synth.hashed_frames(S, H, W, t, pattern=pat, device="cpu", stream_offset=off).numpy()
+            for s in range(S):
+                assert np.array_equal(a[s], bench.np_hashed_frame(off + s, H, W, t, pat)), (pat, s)
+    code = ("import sys, json, io, contextlib; sys.argv=['bench.py','--impl','reference','--workload','vga_rate_inhibition',"
+            "'--steps','3','--warmup','1','--settle','2']; import bench; buf=io.StringIO();\n"
+            "with contextlib.redirect_stdout(buf): bench.main()\n"
+            "line=json.loads(buf.getvalue()); assert line['impl']=='reference' and line['steps']==3 and line['warmup']==1;\n"
+            "assert not any(m.startswith('pydvs_b200') for m in sys.modules), 'reference arm imported the product';\n"
+            "print(json.dumps(line['config']))")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    import argparse
+    import json
+    ref_cfg = json.loads(out.stdout.strip().splitlines()[-1])
+    args = argparse.Namespace(streams=None, scaling="strong", workload="vga_rate_inhibition", pattern="bar",
+                              frame_dtype="int16", ring=4, settle=2)
+    assert ref_cfg == bench.bench_config(args, bench.WORKLOADS["vga_rate_inhibition"], 1)   # both arms print this dict
+
+
+def test_bench_parity_job_detects_a_flipped_pixel():
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    wl = bench.WORKLOADS["vga_rate_inhibition"]
+    H, W = 32, 64
+    ring = [bench.np_hashed_frame(3, H, W, t) for t in range(4)]
+    pipe = bench.oracle_pipeline(wl, W, H)
+    for i in range(6):
+        counts, flat = pipe.step_raw(ring[i % 4])
+    job = {"stream": 3, "wl": wl, "n_frames": 6, "ring": ring, "ref": pipe.ref.copy(), "thr": None,
+           "keys": flat[:, 0].astype(np.int16).copy(), "slot_counts": counts.copy()}
+    r = bench.run_parity_job(job)
+    assert r["ref_equal"] and r["events_equal"] and r["thr_equal"]
+    job["ref"][5, 7] ^= 1
+    assert not bench.run_parity_job(job)["ref_equal"]
