@@ -225,7 +225,7 @@ def test_bench_frame_generators_agree_and_the_reference_arm_never_loads_the_prod
     import json
     ref_cfg = json.loads(out.stdout.strip().splitlines()[-1])
     args = argparse.Namespace(streams=None, scaling="strong", workload="vga_rate_inhibition", pattern="bar",
-                              frame_dtype="int16", ring=4, settle=2)
+                              frame_dtype="int16", ring=16, settle=2)
     assert ref_cfg == bench.bench_config(args, bench.WORKLOADS["vga_rate_inhibition"], 1)   # both arms print this dict
 
 
