@@ -352,7 +352,7 @@ def test_automatic_graph_replay_of_small_steps(adaptive):
     from pydvs_b200 import DVSConfig, DVSStreams, synth
     cfg = DVSConfig(width=96, height=54, streams=5, output_type="TIME" if adaptive else "RATE", max_time_ms=4,
                     adaptive_threshold=adaptive, threshold0=12 if adaptive else None, inh_area_width=0 if adaptive else 2)
-    eager, auto = DVSStreams(cfg, graph=False), DVSStreams(cfg)
+    eager, auto = DVSStreams(cfg, graph=False, event_capacity=5 * 54 * 96 * 4), DVSStreams(cfg, event_capacity=5 * 54 * 96 * 4)
     assert auto.use_graph and not eager.use_graph
     ring = [synth.moving_bar(5, 54, 96, t, noise=6, seed=2) for t in range(3)]
     static = torch.empty_like(ring[0])
