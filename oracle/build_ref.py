@@ -22,6 +22,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = os.environ.get("PYDVS_REFERENCE", "/root/reference")
 OUT = os.path.join(HERE, "_ref", "pydvs")
 MODULES = ("generate_spikes", "generate_spikes_uncoded", "decode_spikes")
+# the reference's only native compute, DVSOperator (pydvs/cpp/dvs_op.cpp:4-33), compiled UNCHANGED against the
+# stand-in OpenCV headers of oracle/opencv_stub/ plus our C-ABI driver oracle/dvs_op_ref_driver.cpp
+DVS_OP_LIB = os.path.join(HERE, "_ref", "libdvs_op_ref.so")
 
 
 def ext_suffix():
@@ -36,8 +39,36 @@ def is_built():
     return all(os.path.exists(p) for p in built_paths())
 
 
+def dvs_op_is_built():
+    return os.path.exists(DVS_OP_LIB)
+
+
+def build_dvs_op(force=False, verbose=True):
+    """g++ on the reference's dvs_op.cpp where it lies (no OpenCV needed: see oracle/opencv_stub).  x86-64 gcc does
+    not contract `relax * ref + diff` into an FMA; -ffp-contract=off states it."""
+    if dvs_op_is_built() and not force:
+        return True
+    cpp_dir = os.path.join(REF_SRC, "pydvs", "cpp")
+    if not os.path.exists(os.path.join(cpp_dir, "dvs_op.cpp")):
+        return dvs_op_is_built()
+    os.makedirs(os.path.dirname(DVS_OP_LIB), exist_ok=True)
+    cc = ["g++", "-std=c++11", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-w", "-I", os.path.join(HERE, "opencv_stub"),
+          "-I", cpp_dir, os.path.join(HERE, "dvs_op_ref_driver.cpp"), os.path.join(cpp_dir, "dvs_op.cpp"), "-o", DVS_OP_LIB]
+    r = subprocess.run(cc, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed for dvs_op.cpp:\n%s\n%s" % (r.stdout, r.stderr))
+    if verbose:
+        print("[oracle/_ref] built", DVS_OP_LIB)
+    return True
+
+
 def build(force=False, verbose=True):
     """Returns True if oracle/_ref is available after the call."""
+    try:
+        build_dvs_op(force=force, verbose=verbose)
+    except Exception as e:   # the Cython modules below do not depend on it
+        if verbose:
+            print("[oracle/_ref] DVSOperator not built: %s" % e)
     if is_built() and not force:
         return True
     src_dir = os.path.join(REF_SRC, "pydvs")

@@ -49,3 +49,34 @@ def load():
         sys.modules.update(saved_sub)
     _cache = (gs, gsu, dec)
     return _cache
+
+
+_dvs_op = None
+
+
+def load_dvs_op():
+    """``ref_dvs_op(src, diff, ref, thr, relax, up, down)``: the reference's own ``DVSOperator::operator()``
+    (``pydvs/cpp/dvs_op.cpp``, compiled unchanged; ``oracle/build_ref.py``) in place on float32 ``[H, W]`` arrays,
+    or ``None`` when it has not been built."""
+    global _dvs_op
+    if _dvs_op is not None:
+        return _dvs_op
+    from . import build_ref
+    if not build_ref.dvs_op_is_built():
+        return None
+    import ctypes as C
+    import numpy as np
+    lib = C.CDLL(build_ref.DVS_OP_LIB)
+    fp = C.POINTER(C.c_float)
+    lib.ref_dvs_op_f32.restype = C.c_int
+    lib.ref_dvs_op_f32.argtypes = [fp, fp, fp, fp, fp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
+
+    def ref_dvs_op(src, diff, ref, thr, relax, up, down):
+        for a in (src, diff, ref, thr):
+            assert a.dtype == np.float32 and a.flags.c_contiguous and a.shape == src.shape and a.ndim == 2
+        ev = np.zeros_like(src)   # the operator advances a pointer into `ev` but never writes it
+        rc = lib.ref_dvs_op_f32(*(a.ctypes.data_as(fp) for a in (src, diff, ref, thr, ev)), relax, up, down,
+                                src.shape[0], src.shape[1])
+        assert rc == 0
+    _dvs_op = ref_dvs_op
+    return _dvs_op

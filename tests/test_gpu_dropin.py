@@ -293,3 +293,37 @@ def test_float_mode_matches_dvs_operator():
         assert np.array_equal(op.thr.cpu().numpy(), thr)
         assert np.array_equal(op.diff.cpu().numpy(), diff)
         np.testing.assert_allclose(op.thr.cpu().numpy(), thr, rtol=1e-6)
+
+
+def test_float_mode_matches_the_reference_built_dvs_operator():
+    """k_step_f32 against planes produced by the reference's own DVSOperator::operator() (pydvs/cpp/dvs_op.cpp compiled
+    unchanged, tests/golden/make_golden_float.py) and, where oracle/_ref travelled, against that library live."""
+    import os
+    from oracle import ref_loader
+    from pydvs_b200 import DVSOperatorF32
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_float_v1.npz"))
+    for name in sorted({k.split("/")[0] for k in g.files}):
+        frames, (thr0, relax, up, down), snaps = g[name + "/frames"], g[name + "/params"], g[name + "/snaps"]
+        n, H, W = frames.shape
+        op = DVSOperatorF32(H, W, streams=1, thr_init=float(thr0), relax=float(relax), up=float(up), down=float(down))
+        dev = torch.from_numpy(frames).cuda()
+        for t in range(n):
+            op.update(dev[t:t + 1].contiguous())
+            if (t + 1) % 10 == 0:
+                exp = snaps[(t + 1) // 10 - 1]
+                for got, e, what in zip((op.diff, op.ref, op.thr), exp, ("diff", "ref", "thr")):
+                    assert np.array_equal(got[0].cpu().numpy().view(np.uint32), e.view(np.uint32)), (name, t, what)
+    live = ref_loader.load_dvs_op()
+    if live is None:
+        return
+    rng = np.random.default_rng(5)
+    S, H, W = 2, 37, 53
+    op = DVSOperatorF32(H, W, streams=S, thr_init=10.0, relax=0.999, up=1.5, down=0.99)
+    ref, thr, diff = (np.zeros((S, H, W), np.float32), np.full((S, H, W), 10.0, np.float32), np.zeros((S, H, W), np.float32))
+    for t in range(120):
+        frame = rng.uniform(0, 255, (S, H, W)).astype(np.float32)
+        for s in range(S):
+            live(frame[s], diff[s], ref[s], thr[s], 0.999, 1.5, 0.99)
+        op.update(torch.from_numpy(frame).cuda())
+    for got, e in zip((op.diff, op.ref, op.thr), (diff, ref, thr)):
+        assert np.array_equal(got.cpu().numpy().view(np.uint32), e.view(np.uint32))

@@ -95,3 +95,22 @@ def test_split_spikes_all_polarities():
         neg, pos, g = O.split_spikes(G["noise_s"], G["noise_a"], pol)
         assert np.array_equal(neg, G["split_p%d_neg" % pol]) and np.array_equal(pos, G["split_p%d_pos" % pol])
         assert g == int(G["split_p%d_g" % pol])
+
+
+def test_float_dvs_operator_golden():
+    """golden_float_v1.npz was produced by the reference's own DVSOperator (tests/golden/make_golden_float.py)."""
+    import os
+    from oracle import oracle as orc
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_float_v1.npz"))
+    names = sorted({k.split("/")[0] for k in g.files})
+    assert len(names) == 3
+    for name in names:
+        frames, (thr0, relax, up, down), snaps = g[name + "/frames"], g[name + "/params"], g[name + "/snaps"]
+        n, H, W = frames.shape
+        ref, thr, diff = np.zeros((H, W), np.float32), np.full((H, W), thr0, np.float32), np.zeros((H, W), np.float32)
+        for t in range(n):
+            orc.dvs_op_f32(np.ascontiguousarray(frames[t]), diff, ref, thr, float(relax), float(up), float(down))
+            if (t + 1) % 10 == 0:
+                exp = snaps[(t + 1) // 10 - 1]
+                for got, e, what in zip((diff, ref, thr), exp, ("diff", "ref", "thr")):
+                    assert np.array_equal(got.view(np.uint32), e.view(np.uint32)), (name, t, what)

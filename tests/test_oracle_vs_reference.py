@@ -104,3 +104,25 @@ def test_numpy_floor_division_and_fp64_history_weight(refs):
     ra, ta = gs.update_reference_rate_adpt(a, s, r, t1, 6, 168, 2, 12, 8, 1.0)
     rb, tb = O.update_reference_rate_adpt(a, s, r, t2, 6, 168, 2, 12, 8, 1.0)
     _eq(ra, rb, "ref"), _eq(np.asarray(ta), np.asarray(tb), "thr")
+
+
+def test_dvs_operator_restatement_matches_the_compiled_reference():
+    """orc_dvs_op_f32 (oracle/dvs_oracle.c) against the reference's own DVSOperator::operator()
+    (pydvs/cpp/dvs_op.cpp:4-33 compiled unchanged against oracle/opencv_stub): bit-identical float32 planes over
+    300 frames per setting, thresholds running up to 1e30 and down to denormals / zero."""
+    from oracle import ref_loader
+    from oracle import oracle as orc
+    op = ref_loader.load_dvs_op()
+    if op is None:
+        pytest.skip("oracle/_ref/libdvs_op_ref.so not built (python oracle/build_ref.py)")
+    rng = np.random.default_rng(11)
+    for (H, W, thr0, relax, up, down, scale) in [(24, 40, 10.0, 0.999, 1.5, 0.99, 255.0), (7, 9, 25.0, 1.0, 2.0, 0.5, 255.0),
+                                                 (16, 16, 1.0, 0.5, 1.01, 0.999, 1.0), (5, 33, 3.0, 0.999, 10.0, 0.1, 1e4)]:
+        a = [np.zeros((H, W), np.float32), np.zeros((H, W), np.float32), np.full((H, W), thr0, np.float32)]
+        b = [x.copy() for x in a]
+        for t in range(300):
+            src = (rng.random((H, W)) * scale).astype(np.float32)
+            op(src, a[0], a[1], a[2], relax, up, down)
+            orc.dvs_op_f32(src, b[0], b[1], b[2], relax, up, down)
+            for x, y, what in zip(a, b, ("diff", "ref", "thr")):
+                assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), (t, what)
