@@ -2,7 +2,7 @@
 """The offline conversion flow of the reference's ``mnist_to_spikes.py`` (images -> micro-saccade frames -> DVS ->
 time-binary AER -> one text spike file per image), with every stage on the GPU and all images converted at once:
 
-    VirtualCam (batched, deterministic)  ->  DVSStreams (fused step, state in HBM)  ->  SpikeFileWriter
+    SaccadeSource (batched micro-saccades)  ->  DVSStreams (fused step, state in HBM)  ->  SpikeFileWriter
 
     python examples/images_to_spike_files.py --out /tmp/spikes          # synthetic 32x32 digit-like blobs
 
@@ -19,7 +19,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pydvs_b200 import DVSConfig, DVSStreams  # noqa: E402
 from pydvs_b200.sinks import SpikeFileWriter, spike_file_lines_all_streams  # noqa: E402
-from pydvs_b200.virtual_cam import VirtualCam  # noqa: E402
+from pydvs_b200.frame_sources import SaccadeSource  # noqa: E402
 
 
 def blob_images(n, size=32, seed=0):
@@ -45,8 +45,8 @@ def convert(images, frames=10, fps=100, seed=0, key_bits=(10, 5, 31)):
     images = torch.as_tensor(images, dtype=torch.int16, device="cuda")
     n, h, w = images.shape
     frame_ms = int(1000. / fps)
-    cam = VirtualCam(images, behaviour=VirtualCam.BEHAVE_MICROSACCADE, fps=fps, image_on_time_ms=frames * 1000. / fps * 4,
-                     streams=n, start_index=np.arange(n), seed=seed, max_cycles=1)
+    # the frame loop of mnist_to_spikes.py:246-258 (it calls the animator directly, not VirtualCam.read) for all images
+    cam = SaccadeSource(images, np.arange(n, dtype=np.int32), frames_per_image=frames, seed=seed)
     dvs = DVSStreams(DVSConfig(width=w, height=h, streams=n, output_type="TIME_BIN_THR", adaptive_threshold=True,
                                threshold=12, min_threshold=6, max_threshold=168, threshold_delta_down=2,
                                threshold_delta_up=12, history_weight=0.99, max_time_ms=frame_ms, num_bins=6, ref0=0,
@@ -54,11 +54,8 @@ def convert(images, frames=10, fps=100, seed=0, key_bits=(10, 5, 31)):
                      event_capacity=n * h * w * 8)
     writers = [SpikeFileWriter(frame_ms, max(1, frame_ms // 6)) for _ in range(n)]
     flag_shift, data_shift, data_mask = key_bits
-    for _ in range(frames):
-        ok, batch = cam.read()
-        if not ok:
-            break
-        res = dvs.step(batch)
+    for f in range(frames):
+        res = dvs.step(cam.frame(f))
         # one key launch + two device-to-host copies for all images of the frame
         lines = spike_file_lines_all_streams(res, flag_shift, data_shift, data_mask, writers[0].t, writers[0].t_bin_ms)
         for s in range(n):

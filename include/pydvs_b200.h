@@ -250,6 +250,15 @@ int dvs_move_mask_i16(const int16_t *images, int32_t n_images, const int32_t *im
                       const int32_t *dy, int32_t bg, const double *mask, int16_t *out, int32_t S, int32_t H,
                       int32_t W, void *stream);
 
+/* The saccade search of attention_image gs:1246-1298 for S square cameras of width W (even): tiny = 2x2 area
+ * means (cv2.resize INTER_AREA on int16: (sum + 2) >> 2) of the previous frame and of the DVS reference plane,
+ * diff = |tiny_prev - tiny_ref| in int16, top_n = the five largest cells in ascending (value, index) order,
+ * max_idx = top_n[picks[s]] (the reference draws picks from np.random.randint(5)); cx[s], cy[s] receive the new
+ * image centre (new_w - col, new_w - row; 0, 0 when outside [-new_w, new_w]).  Equal diff values: the reference's
+ * np.argsort leaves their order unspecified; here they are ordered by cell index. */
+int dvs_attention_targets_i16(const int16_t *prev, const int16_t *ref, const int32_t *picks, int32_t *cx,
+                              int32_t *cy, int32_t S, int32_t W, void *stream);
+
 /* ---- rows either side of the path ---------------------------------------------- */
 
 /* Float32 NVS variants, pydvs/numba_nvs.py ("nvs").  One fused pass, in place on ref/thr (and the OFF

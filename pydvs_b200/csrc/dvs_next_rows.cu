@@ -373,9 +373,92 @@ int launch_status(const char *what) {
 }
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// attention_image gs:1246-1298, the saccade search, for S cameras at once: one CTA per stream.
+//   tiny_x  = cv2.resize(x, (new_w, new_w), INTER_AREA)  -> for int16 at exactly 2x: (sum of the 2x2 block + 2) >> 2
+//   diff    = np.abs(tiny_prev - tiny_ref)               -> int16 arithmetic (wraps like NumPy)
+//   top_n   = np.argsort(diff.reshape(-1))[-5:]          -> the five largest (value, index) pairs in ascending order;
+//                                                           NumPy's default sort leaves the order of EQUAL values
+//                                                           unspecified -- here ties are ordered by index (stable sort)
+//   max_idx = top_n[pick]; row, col = (max_idx // new_w) * 2, (max_idx % new_w) * 2
+//   cx, cy  = new_w - col, new_w - row  (reset to 0, 0 when outside [-new_w, new_w])
+// Selection: five rounds of a block-wide arg-max over 64-bit keys (value + 32768) << 32 | index, each round bounded
+// above by the previous winner.
+__device__ __forceinline__ int att_w16(int x) { return (int)(short)x; }
+__global__ void __launch_bounds__(256) k_attention_targets(const int16_t *__restrict__ prev, const int16_t *__restrict__ ref,
+                                                           const int32_t *__restrict__ picks, int32_t *__restrict__ cx,
+                                                           int32_t *__restrict__ cy, int Wd) {
+  __shared__ unsigned long long warp_best[8];
+  __shared__ unsigned long long chosen[5];
+  const int s = blockIdx.x, new_w = Wd >> 1, cells = new_w * new_w;
+  const int16_t *p = prev + (size_t)s * Wd * Wd, *r = ref + (size_t)s * Wd * Wd;
+  auto key_of = [&](int cell) -> unsigned long long {
+    const int row = (cell / new_w) * 2, col = (cell % new_w) * 2;
+    const int16_t *pp = p + (size_t)row * Wd + col, *rr = r + (size_t)row * Wd + col;
+    const int tp = att_w16(((int)pp[0] + pp[1] + pp[Wd] + pp[Wd + 1] + 2) >> 2);
+    const int tr = att_w16(((int)rr[0] + rr[1] + rr[Wd] + rr[Wd + 1] + 2) >> 2);
+    const int d = att_w16(tp - tr);
+    const int a = att_w16(d < 0 ? -d : d);
+    return ((unsigned long long)(unsigned)(a + 32768) << 32) | (unsigned)cell;
+  };
+  unsigned long long bound = ~0ull;
+  for (int round = 0; round < 5; ++round) {
+    unsigned long long best = 0ull;  // keys are > 0 only when a cell qualifies: (a + 32768) << 32 >= 0, cell 0 with a = -32768 is key 0
+    bool have = false;
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+      const unsigned long long k = key_of(c);
+      if (k < bound && (!have || k > best)) { best = k; have = true; }
+    }
+    // encode "nothing" as bound itself cannot win: use k + 1 so that 0 means none
+    unsigned long long v = have ? best + 1 : 0ull;
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long y = __shfl_xor_sync(0xffffffffu, v, o);
+      if (y > v) v = y;
+    }
+    if ((threadIdx.x & 31) == 0) warp_best[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long m = 0ull;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = warp_best[w] > m ? warp_best[w] : m;
+      chosen[round] = m;  // 0 = fewer than 5 cells
+    }
+    __syncthreads();
+    if (chosen[round] == 0ull) break;
+    bound = chosen[round] - 1;
+  }
+  if (threadIdx.x == 0) {
+    // top_n is ascending: top_n[4] is round 0's winner.  Fewer than five cells: NumPy's [-5:] keeps them all.
+    int n_top = 0;
+    while (n_top < 5 && n_top < cells) ++n_top;
+    const int pick = picks[s];
+    int idx_in_top = pick;                       // index into the ascending list of n_top entries
+    if (idx_in_top < 0) idx_in_top += n_top;     // Python negative index
+    int new_cx = 0, new_cy = 0;
+    if (idx_in_top >= 0 && idx_in_top < n_top) {
+      const unsigned long long k = chosen[n_top - 1 - idx_in_top] - 1;
+      const int max_idx = (int)(unsigned)(k & 0xffffffffull);
+      const int row = (max_idx / new_w) * 2, col = (max_idx % new_w) * 2;
+      new_cx = new_w - col;
+      new_cy = new_w - row;
+      if (new_cx > new_w || new_cx < -new_w || new_cy > new_w || new_cy < -new_w) { new_cx = 0; new_cy = 0; }
+    }
+    cx[s] = new_cx;
+    cy[s] = new_cy;
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int dvs_attention_targets_i16(const int16_t *prev, const int16_t *ref, const int32_t *picks, int32_t *cx, int32_t *cy,
+                              int32_t S, int32_t W, void *stream) {
+  if (!prev || !ref || !picks || !cx || !cy || S <= 0 || W < 2 || (W & 1))
+    return dvs::set_error(DVS_ERR_INVALID_ARGUMENT, "attention_targets: square frames of even width, one pick per stream");
+  k_attention_targets<<<(unsigned)S, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(prev, ref, picks, cx, cy, W);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return dvs::set_error((int)e, cudaGetErrorString(e));
+  return DVS_OK;
+}
 
 int dvs_nvs_step_f32(const dvs_nvs_params *p, void *stream) {
   if (!p || !p->frame || !p->ref || !p->thr || !p->spikes || p->n_px < 0)

@@ -254,10 +254,11 @@ def test_traverse_and_fade_random_vs_oracle():
 
 
 # ---- deterministic batched VirtualCam --------------------------------------------------------------------
-@pytest.mark.parametrize("behaviour", ["SACCADE", "TRAVERSE", "FADE", "NONE"])
+@pytest.mark.parametrize("behaviour", ["SACCADE", "TRAVERSE", "FADE", "NONE", "ATTENTION"])
 @pytest.mark.parametrize("with_mask", [False, True])
 def test_virtual_cam_schedule_matches_scalar_restatement(behaviour, with_mask):
-    from oracle.virtual_cam_oracle import VirtualCamOracle
+    # the restatement is pinned against the reference's own VirtualCam class (tests/test_virtual_cam_reference.py)
+    from oracle.virtual_cam_oracle import ReplayDraws, VirtualCamOracle
     from pydvs_b200.virtual_cam import VirtualCam
     rng = np.random.default_rng(4)
     N, H, W, S = 3, 32, 32, 5
@@ -265,24 +266,73 @@ def test_virtual_cam_schedule_matches_scalar_restatement(behaviour, with_mask):
     mask = rng.uniform(0, 1, (H, W)) if with_mask else None
     start = np.array([0, 1, 2, 1, 0])
     kw = dict(fps=30, image_on_time_ms=400, inter_off_time_ms=100, max_saccade_distance=2,
-              frames_per_microsaccade=2, max_cycles=2, background_gray=9)
+              frames_per_microsaccade=2, max_cycles=2, background_gray=9, frames_per_saccade=5)
     cam = VirtualCam(_cu(imgs), behaviour=behaviour, fade_mask=mask, streams=S, start_index=start, seed=11, **kw)
-    refs = [VirtualCamOracle(imgs, behaviour, fade_mask=mask, start_index=int(start[s]),
-                             rng=np.random.RandomState(11 + s), **kw) for s in range(S)]
+    replay = ReplayDraws(11, S)      # the same vectorised draws, handed out one camera at a time
+    refs = [VirtualCamOracle(imgs, behaviour, fade_mask=mask, start_index=int(start[s]), rng=replay.stream(s), **kw)
+            for s in range(S)]
     n_valid = 0
     for step in range(140):
-        ok, frames = cam.read()
+        dvs_ref = rng.integers(0, 256, (S, H, W)).astype(np.int16)    # stands in for the DVS reference planes (ATTENTION)
+        ok, frames = cam.read(_cu(dvs_ref))
         host = frames.cpu().numpy()
+        centers = cam.center
         for s in range(S):
-            ok_ref, img = refs[s].read()
+            ok_ref, img = refs[s].read(dvs_ref[s])
             assert ok == ok_ref, (step, s)
             assert np.array_equal(host[s], img), (behaviour, step, s)
+            if behaviour in ("SACCADE", "ATTENTION"):
+                assert tuple(centers[s]) == (refs[s].cx, refs[s].cy), (step, s)
         n_valid += ok
         if not ok and behaviour != "NONE":
             break
     assert n_valid > 50
     if behaviour != "NONE":
         assert not ok   # max_cycles reached: the camera reports end of stream and serves the background
+
+
+def test_virtual_cam_replays_the_reference_class_recordings():
+    """tests/golden/golden_vcam_v1.npz holds what the reference's own VirtualCam class served on its mnist/t10k fixtures
+    (tests/golden/make_golden_vcam.py) together with the random draws it made; the GPU camera fed the same draws must
+    serve the same frames.  ATTENTION frames whose five largest changes are tied are unspecified in the reference."""
+    import os
+    from pydvs_b200.virtual_cam import VirtualCam
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_vcam_v1.npz"))
+    fps, on_ms, off_ms, max_dist, fp_usacc, fp_sacc, cycles, bg = (int(v) for v in g["args"])
+    images, mask = g["images"], g["mask"]
+
+    class Recorded:
+        def __init__(self, steps, picks):
+            self.steps, self.pk, self.i, self.j = steps, picks, 0, 0
+
+        def offsets(self, S, d):
+            self.i += 1
+            return self.steps[self.i - 1:self.i]
+
+        def picks(self, S):
+            self.j += 1
+            return self.pk[self.j - 1:self.j]
+
+    for name in sorted({k.split("/")[0] for k in g.files if "/" in k}):
+        behaviour, masked = name.split("_")[0], name.endswith("_mask")
+        frames, valid, centers = g[name + "/frames"], g[name + "/valid"], g[name + "/centers"]
+        tied = set(int(i) for i in g[name + "/tied_at"])
+        cam = VirtualCam(_cu(images), behaviour=behaviour, fps=fps, image_on_time_ms=on_ms, inter_off_time_ms=off_ms,
+                         max_saccade_distance=max_dist, frames_per_microsaccade=fp_usacc, frames_per_saccade=fp_sacc,
+                         max_cycles=cycles, background_gray=bg, fade_mask=mask if masked else None, streams=1,
+                         draws=Recorded(g[name + "/steps"], g[name + "/picks"]))
+        compared = 0
+        for i in range(len(frames)):
+            ref = _cu(g[name + "/ref_planes"][i][None]) if behaviour == "ATTENTION" else None
+            ok, fr = cam.read(ref)
+            assert bool(ok) == bool(valid[i]), (name, i)
+            if i in tied and tuple(cam.center[0]) != tuple(centers[i]):
+                cam.cx[:], cam.cy[:] = int(centers[i][0]), int(centers[i][1])
+                cam.current_image = _cu(frames[i][None])
+                continue
+            assert np.array_equal(fr[0].cpu().numpy(), frames[i]), (name, i)
+            compared += 1
+        assert compared >= len(frames) - 6, name
 
 
 def test_virtual_cam_attention_runs_and_recentres():
@@ -301,11 +351,13 @@ def test_virtual_cam_attention_runs_and_recentres():
 # ---- the whole offline flow: frame source -> fused step -> spike files -----------------------------------
 def test_images_to_spike_files_matches_the_cpu_restatement():
     """examples/images_to_spike_files.py (mnist_to_spikes.py's flow, batched on the GPU) against the same flow on the
-    CPU: scalar VirtualCam restatement -> oracle pipeline -> the reference's writer loop."""
+    CPU: the script's micro-saccade loop restated with the pinned move_image -> oracle pipeline -> the reference's
+    writer loop."""
     import importlib.util
     import os
     from oracle import oracle as orc
-    from oracle.virtual_cam_oracle import VirtualCamOracle
+    from oracle import frame_oracle as fo
+    from pydvs_b200.frame_sources import saccade_offsets
     import pydvs_b200.generate_spikes as gs
     spec = importlib.util.spec_from_file_location(
         "_example", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "images_to_spike_files.py"))
@@ -317,16 +369,14 @@ def test_images_to_spike_files_matches_the_cpu_restatement():
     frame_ms = int(1000. / fps)
     lut = gs.generate_log2_table(2, 8)[1]
     total = 0
+    offsets = saccade_offsets(n, frames, 1, 1, seed=5)      # mnist_to_spikes.py:246-258 with seeded draws
     for s in range(n):
-        cam = VirtualCamOracle(list(imgs), "SACCADE", fps, frames * 1000. / fps * 4, 100, 1, 1, 1, None, 0, s,
-                               np.random.RandomState(5 + s))
         pipe = orc.Pipeline(32, 32, mode=orc.ENC_TIME_BIN_THR, threshold=12, max_time_ms=frame_ms, num_bins=6,
                             history_weight=0.99, adaptive=True, min_thr=6, max_thr=168, down=2, up=12, lut=lut,
                             flag_shift=10, data_shift=5, data_mask=31, ref0=0, thr0=12)
         lines, t = [], 0
-        for _ in range(frames):
-            ok, frame = cam.read()
-            assert ok
+        for f in range(frames):
+            frame = fo.move_image(imgs[s], int(offsets[f, s, 0]), int(offsets[f, s, 1]), 0)
             t_idx = 0
             for slot in pipe.step(frame):                  # mnist_to_spikes.py:290-303
                 for key in slot:
