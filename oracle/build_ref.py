@@ -39,6 +39,49 @@ def is_built():
     return all(os.path.exists(p) for p in built_paths())
 
 
+# the reference's CALLERS of the path, byte-compiled from the sources where they lie (bytecode is build output, like the
+# .so files above): tests run them unchanged on top of the drop-in module to show that callers need no edits
+CALLERS_DIR = os.path.join(HERE, "_ref", "callers")
+CALLERS = {"stand_alone": "stand_alone.py", "virtual_cam": os.path.join("pydvs", "virtual_cam.py")}
+
+
+def caller_path(name):
+    return os.path.join(CALLERS_DIR, name + ".pyc")
+
+
+def callers_are_built():
+    return all(os.path.exists(caller_path(n)) for n in CALLERS)
+
+
+def build_callers(force=False, verbose=True):
+    """py_compile the reference's stand_alone.py and pydvs/virtual_cam.py into oracle/_ref/callers/*.pyc.  `dfile`
+    makes the code objects report a path inside that directory, which is where virtual_cam.py looks for its
+    fading_mask.png (virtual_cam.py:113-115; tests write that fixture there from their golden arrays)."""
+    if callers_are_built() and not force:
+        return True
+    if not all(os.path.exists(os.path.join(REF_SRC, rel)) for rel in CALLERS.values()):
+        return callers_are_built()
+    import py_compile
+    os.makedirs(CALLERS_DIR, exist_ok=True)
+    for name, rel in CALLERS.items():
+        py_compile.compile(os.path.join(REF_SRC, rel), cfile=caller_path(name), dfile=os.path.join(CALLERS_DIR, name + ".py"),
+                           doraise=True)
+        if verbose:
+            print("[oracle/_ref] byte-compiled", caller_path(name))
+    return True
+
+
+def load_caller_code(name):
+    """The code object of a byte-compiled reference caller (or None)."""
+    import marshal
+    path = caller_path(name)
+    if not os.path.exists(path):
+        return None
+    with open(path, "rb") as f:
+        data = f.read()
+    return marshal.loads(data[16:])
+
+
 def dvs_op_is_built():
     return os.path.exists(DVS_OP_LIB)
 
@@ -69,6 +112,11 @@ def build(force=False, verbose=True):
     except Exception as e:   # the Cython modules below do not depend on it
         if verbose:
             print("[oracle/_ref] DVSOperator not built: %s" % e)
+    try:
+        build_callers(force=force, verbose=verbose)
+    except Exception as e:
+        if verbose:
+            print("[oracle/_ref] callers not byte-compiled: %s" % e)
     if is_built() and not force:
         return True
     src_dir = os.path.join(REF_SRC, "pydvs")

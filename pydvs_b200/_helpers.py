@@ -211,7 +211,7 @@ def build_helpers(uncoded):
             return torch.from_numpy(small).to(o.device)
 
         diff = (area_half(p) - area_half(r)).abs()
-        top_n = torch.argsort(diff.reshape(-1))[-5:]
+        top_n = torch.argsort(diff.reshape(-1), stable=True)[-5:]   # equal values: by index (NumPy leaves it unspecified)
         max_idx = int(top_n[np.random.randint(5)].item())
         row, col = (max_idx // new_w) * 2, (max_idx % new_w) * 2
         center_x, center_y = new_w - col, new_w - row
