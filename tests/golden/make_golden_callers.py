@@ -14,7 +14,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import build_ref, ref_loader  # noqa: E402
-from tests import _callers  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import _callers  # noqa: E402
 
 N_FRAMES = 60
 

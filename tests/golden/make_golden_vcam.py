@@ -13,7 +13,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from tests import _vcam_ref as R  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import _vcam_ref as R  # noqa: E402
 from oracle.virtual_cam_oracle import VirtualCamOracle  # noqa: E402
 
 

@@ -14,7 +14,7 @@ import pytest
 import torch
 
 from oracle import build_ref
-from tests import _callers
+import _callers
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))

@@ -94,3 +94,41 @@ def test_float_mode_4k_linearity_of_quiet_pixels():
     for _ in range(3):
         op.update(frame)
     assert torch.all(op.ref == 8.0) and torch.all(op.diff == 0) and torch.all(op.thr == 1e9)
+
+
+@pytest.mark.parametrize("workload", ["4k_rate_inhibition", "1080p_time_adaptive", "4k_dense"])
+def test_repeated_steps_are_byte_identical(workload):
+    """Determinism stress (stands in for racecheck, which is closed on this pool): the same multi-stream step from the
+    same state, 50 times, must produce byte-identical events, CSR row pointers, reference and threshold planes --
+    shared-memory histograms, atomics into the redo list and the ordered compaction leave no room for run-to-run order."""
+    from pydvs_b200 import DVSConfig, DVSStreams, synth
+    if workload == "1080p_time_adaptive":
+        S, H, W = 16, 1080, 1920
+        cfg = DVSConfig(width=W, height=H, streams=S, output_type="TIME", max_time_ms=4, num_bins=4,
+                        adaptive_threshold=True, threshold0=12)
+    else:
+        S, H, W = 16, 2160, 3840
+        cfg = DVSConfig(width=W, height=H, streams=S, output_type="RATE", max_time_ms=8, inh_area_width=2)
+    pattern = "dense" if workload == "4k_dense" else "bar"
+    dvs = DVSStreams(cfg, event_capacity=S * H * W * (2 if pattern == "dense" else 1), graph=False)
+    for t in range(6):     # leave the start-up transient (the generic body handles its overfull tiles) but keep spikes
+        dvs.step(synth.hashed_frames(S, H, W, t, pattern=pattern))
+    frame = synth.hashed_frames(S, H, W, 6, pattern=pattern)
+    ref0 = dvs.ref.clone()
+    thr0 = dvs.thr.clone() if dvs.thr is not None else None
+    first = None
+    for rep in range(50):
+        dvs.ref.copy_(ref0)
+        if thr0 is not None:
+            dvs.thr.copy_(thr0)
+        res = dvs.step(frame)
+        n = res.total_events()
+        got = (res.seg_offsets.clone(), res.events_raw[:n].clone(), dvs.ref.clone(),
+               dvs.thr.clone() if thr0 is not None else None)
+        if first is None:
+            first = got
+            assert n > 1000
+            continue
+        for a, b, what in zip(first, got, ("seg_offsets", "events", "ref", "thr")):
+            assert a is None or torch.equal(a, b), (workload, rep, what)
+    dvs.check_status()

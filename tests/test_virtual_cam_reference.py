@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle.virtual_cam_oracle import VirtualCamOracle, attention_target
-from tests import _vcam_ref as R
+import _vcam_ref as R
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_vcam_v1.npz")
 
