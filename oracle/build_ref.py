@@ -46,7 +46,8 @@ CALLERS = {"stand_alone": "stand_alone.py", "virtual_cam": os.path.join("pydvs",
 
 
 def caller_path(name):
-    return os.path.join(CALLERS_DIR, name + ".pyc")
+    return os.path.join(CALLERS_DIR, name + ".code")   # CPython bytecode (py_compile layout); not named .pyc so that
+    #                                                      snapshot tools that skip *.pyc still carry it to the GPU box
 
 
 def callers_are_built():
@@ -54,7 +55,7 @@ def callers_are_built():
 
 
 def build_callers(force=False, verbose=True):
-    """py_compile the reference's stand_alone.py and pydvs/virtual_cam.py into oracle/_ref/callers/*.pyc.  `dfile`
+    """py_compile the reference's stand_alone.py and pydvs/virtual_cam.py into oracle/_ref/callers/*.code.  `dfile`
     makes the code objects report a path inside that directory, which is where virtual_cam.py looks for its
     fading_mask.png (virtual_cam.py:113-115; tests write that fixture there from their golden arrays)."""
     if callers_are_built() and not force:

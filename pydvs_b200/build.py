@@ -37,7 +37,8 @@ def _digest():
         path = name if os.path.isabs(name) else os.path.join(CSRC, name)
         with open(path, "rb") as f:
             h.update(name.encode() + b"\0" + f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    # flags without the absolute include paths: the same tree built elsewhere (the GPU box) has the same digest
+    h.update(" ".join(f for f in NVCC_FLAGS if not os.path.isabs(f)).encode())
     return h.hexdigest()
 
 
