@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpydvs_b200.so")
+# PYDVS_B200_LIB selects another build of the same library (kernel tuning experiments: tools/build_variant.py)
+LIB_PATH = os.environ.get("PYDVS_B200_LIB") or os.path.join(_HERE, "libpydvs_b200.so")
 
 # error codes / enums of the header
 OK = 0

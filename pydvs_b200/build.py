@@ -36,7 +36,7 @@ def _digest():
     for name in files:
         path = name if os.path.isabs(name) else os.path.join(CSRC, name)
         with open(path, "rb") as f:
-            h.update(name.encode() + b"\0" + f.read())
+            h.update(os.path.basename(name).encode() + b"\0" + f.read())
     # flags without the absolute include paths: the same tree built elsewhere (the GPU box) has the same digest
     h.update(" ".join(f for f in NVCC_FLAGS if not os.path.isabs(f)).encode())
     return h.hexdigest()

@@ -41,11 +41,26 @@ constexpr int kFastCap = 2048;  // work-list capacity; denser tiles go to the ge
 // One tile.  STAGED: the tile's frame / reference rows were brought into shared memory by a bulk async copy
 // (st_cur / st_ref); after the first barrier every thread holds its pixels in registers, so the stage buffer
 // is dead and doubles as work list + record staging (smem_raw points at it; `ctl` holds wtot / hist).
-template <int SRC, int JH, bool PAIR, bool SIMPLE, bool ADAPT, bool STAGED>
+// ENC: 0 = any encoder / polarity / update the fast path takes (work-list entries carry reference and abs_diff);
+//      1 = coded RATE encoder, 2 = coded TIME encoder -- MERGED lists, history_weight == 1, rate (or rate_adpt) update,
+//      inlined membership / slot / histogram.  For ENC != 0 the work list holds only the 16-bit tile-local pixel index
+//      (plus the old threshold when ADAPT): the lane that takes a candidate re-reads its frame and reference pixel
+//      (two 2-byte loads that hit L1 / L2, the tile was just streamed in) instead of the pushing thread extracting
+//      them from its packed registers -- the push was the most divergent part of the kernel (a warp runs it as often
+//      as its busiest lane has candidates), so the work moves to the phase that is spread evenly over the lanes.
+enum { ENC_ANY = 0, ENC_RATE_CODED = 1, ENC_TIME_CODED = 2 };
+// a // thr for 0 <= a <= 255 and thr >= 0 (NumPy: x // 0 == 0): (a + 0.5) * rcp(thr) truncates to the exact quotient,
+// the nearest integer boundary is >= 0.5 / (a + 1) >= 2^-9 away in relative terms, far above the rcp / product error
+DEV int adpt_div(int a, int thr) {
+  return thr == 0 ? 0 : (int)(((float)a + 0.5f) * __frcp_rn((float)thr));
+}
+template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT, bool STAGED>
 DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigned char *smem_raw, unsigned char *ctl,
                     const unsigned char *st_cur, const unsigned char *st_ref) {
   constexpr int J = PAIR ? 2 * JH : JH;
+  constexpr bool SIMPLE = ENC != ENC_ANY;
   uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
+  uint16_t *wl16 = reinterpret_cast<uint16_t *>(smem_raw);  // ENC != 0: pixel indices only
   uint2 *rec_sm = reinterpret_cast<uint2 *>(smem_raw + kFastCap * 4);
   uint32_t *wtot = reinterpret_cast<uint32_t *>(ctl);
   uint16_t *wl_thr = reinterpret_cast<uint16_t *>(wtot + 128 + 2 * (A.enc.mode == DVS_ENC_NONE ? 0 : A.enc.n_slots + 1) + 8);  // ADAPT
@@ -115,6 +130,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   const uint32_t kadd = (uint32_t)(0x7fff - T) * 0x00010001u;  // bit 15 of (a + kadd) <=> a > T
   uint32_t flags8[J];
   uint32_t rng = 0, cnt_lo = 0, cnt_hi = 0;  // counts of groups (0,1) and (2,3), 16-bit fields
+  uint32_t tmax = 0;                         // ADAPT: lane-wise maximum of the thresholds of this thread
   // abs_diff of a word of two pixels, kept only where the pixel spikes (abs_diff * spikes, gs:73-75); recomputed
   // where it is needed instead of being held in registers across the phases
   auto masked_abs = [&](int j, int w) -> uint32_t {
@@ -135,13 +151,19 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       if (ADAPT) fl[w] = ~((t_pk[j][w] | 0x80008000u) - a) & 0x80008000u;  // a > threshold lane-wise (both < 2^15)
       else fl[w] = (a + kadd) & 0x80008000u;                 // spike flags at bits 15 / 31
     }
-    if (ADAPT) rng |= ((t_pk[j][0] | t_pk[j][1] | t_pk[j][2]) | t_pk[j][3]) & 0x80008000u ? 0xFF00u : 0u;  // negative threshold
+    if (ADAPT) tmax = __vmaxu2(tmax, __vmaxu2(__vmaxu2(t_pk[j][0], t_pk[j][1]), __vmaxu2(t_pk[j][2], t_pk[j][3])));
     rng |= (r_pk[j][0] | r_pk[j][1] | r_pk[j][2]) | r_pk[j][3];
     if (SRC != SRC_U8) rng |= (c_pk[j][0] | c_pk[j][1] | c_pk[j][2]) | c_pk[j][3];
     if (fl[0] | fl[1] | fl[2] | fl[3]) {
 #pragma unroll
       for (int w = 0; w < 4; ++w) flags8[j] |= (((fl[w] >> 15) & 1u) | ((fl[w] >> 30) & 2u)) << (2 * w);
     }
+  }
+  if (ADAPT) {
+    // a negative threshold (bit 15 as an unsigned lane), or -- coded rule -- one so large that th + up leaves int16
+    // and wraps negative in the reference (gs:292): the generic body replays those tiles with exact int16 arithmetic
+    const uint32_t over = A.upd.uncoded ? tmax : (tmax | (tmax + (uint32_t)A.upd.thr_up * 0x00010001u));
+    if (over & 0x80008000u) rng |= 0xFF00u;
   }
   if (PAIR) {
     // local_inhibition gs:177-221 on registers: of each 2x2 area (word w of the upper and of the lower
@@ -183,14 +205,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
         uint32_t t_dn, t_up = 0;
         if (!A.upd.uncoded) {
           t_dn = __vminu2(__vmaxu2(th, mnd2) - dn2, mx2);                // clip(th - down, min, max)
-          if (flags8[j]) {
-            // clip(th + up, min, max) on int16 lanes: a sum above 32767 wraps negative in the reference (gs:292)
-            // and therefore clips to min
-            const uint32_t su = th + up2;  // th, up <= 32767: no carry between the lanes
-            t_up = __vminu2(__vmaxu2(su, mn2), mx2);
-            const uint32_t wrapped = ((su & 0x80008000u) >> 15) * 0xffffu;
-            t_up = (t_up & ~wrapped) | (mn2 & wrapped);
-          }
+          if (flags8[j]) t_up = __vminu2(__vmaxu2(th + up2, mn2), mx2);  // clip(th + up, min, max); th + up <= 32767 (range vote)
         } else {
           // uncoded twin gsu:286-295: += up only while th < max, -= down only while th > min, no clip.
           // lane-wise compare of values < 2^15: bit 15 of ((x | 0x8000) - y) is set iff x >= y
@@ -275,7 +290,42 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     for (int j = 0; j < J; ++j)
       pos_of[j] = __reduce_add_sync(kFull, lane < j * NW + warp ? ent : 0u) +  // candidates of earlier (group, warp) pairs
                   (((j < 2 ? ex_lo : ex_hi) >> (16 * (j & 1))) & 0xffffu);
-    if (PAIR) {
+    if (SIMPLE && PAIR) {
+      // index-only entries: one 16-bit store per surviving area
+#pragma unroll
+      for (int h = 0; h < JH; ++h) {
+        const int ju = h, jl = JH + h;
+        if ((flags8[ju] | flags8[jl]) == 0) continue;
+        const int qu = q0_of(ju), ql = q0_of(jl);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t bu = (flags8[ju] >> (2 * w)) & 3u, bl = (flags8[jl] >> (2 * w)) & 3u;
+          if ((bu | bl) == 0) continue;
+          const bool up = bu != 0;
+          const int half = (int)((up ? bu : bl) >> 1);
+          const uint32_t pos = up ? pos_of[ju] : pos_of[jl];
+          if (ADAPT) wl_thr[pos] = (uint16_t)((up ? t_pk[ADAPT ? ju : 0][w] : t_pk[ADAPT ? jl : 0][w]) >> (16 * half));
+          wl16[pos] = (uint16_t)((up ? qu : ql) + 2 * w + half);
+          if (up) pos_of[ju] = pos + 1; else pos_of[jl] = pos + 1;
+        }
+      }
+    } else if (SIMPLE) {
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        if (flags8[j] == 0) continue;
+        const int q0 = q0_of(j);
+        uint32_t pos = pos_of[j];
+        for (uint32_t m = flags8[j]; m; m &= m - 1) {  // candidates only
+          const int p = __ffs(m) - 1;
+          if (ADAPT) {
+            const unsigned long long t_lo = ((unsigned long long)t_pk[ADAPT ? j : 0][1] << 32) | t_pk[ADAPT ? j : 0][0],
+                                     t_hi = ((unsigned long long)t_pk[ADAPT ? j : 0][3] << 32) | t_pk[ADAPT ? j : 0][2];
+            wl_thr[pos] = (uint16_t)((p < 4 ? t_lo : t_hi) >> (16 * (p & 3)));
+          }
+          wl16[pos++] = (uint16_t)(q0 + p);
+        }
+      }
+    } else if (PAIR) {
       // after the 2x2 inhibition an area (word w of the upper and of the lower row group) holds at most one
       // candidate: walk the four areas of a column block once, instead of the set bits of each row group
 #pragma unroll
@@ -337,12 +387,25 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     bool tp = false, tn = false;
     uint2 rec = make_uint2(0u, 0u);
     if (i < hi) {
-      const uint32_t e = wl[i];
-      const int q = e & 0x1fff, r = (e >> 13) & 0xff, a = (e >> 21) & 0xff;
-      const bool neg = (e >> 29) & 1u;
+      int q, r, a;
+      bool neg;
+      if (SIMPLE) {  // index-only entry: fetch the pixel again (both values are in [0, 255]: the tile passed the range vote)
+        q = wl16[i];
+        // the tile's frame pointer is rebuilt from the reference pointer (kernel parameters are free, live registers are not)
+        const long long boff = reinterpret_cast<const char *>(ref_t) - reinterpret_cast<const char *>(A.ref);
+        const unsigned char *cur_q = static_cast<const unsigned char *>(A.curr) + (SRC == SRC_U8 ? (boff >> 1) + q : boff + 2 * q);
+        const int c = SRC == SRC_U8 ? (int)__ldg(cur_q) : (int)__ldg(reinterpret_cast<const uint16_t *>(cur_q));
+        r = (int)reinterpret_cast<const uint16_t *>(ref_t)[q];
+        neg = c < r;
+        a = neg ? r - c : c - r;
+      } else {
+        const uint32_t e = wl[i];
+        q = e & 0x1fff; r = (e >> 13) & 0xff; a = (e >> 21) & 0xff;
+        neg = (e >> 29) & 1u;
+      }
       const int y = (int)__umulhi((unsigned)q, A.inv_w), x = q - y * A.W;
       int upd;
-      if (ADAPT) upd = np_floordiv(a, (int)wl_thr[i]);                       // gs:287-289: (a // thr) [* min_threshold below]
+      if (ADAPT) upd = SIMPLE ? adpt_div(a, (int)wl_thr[i]) : np_floordiv(a, (int)wl_thr[i]);  // gs:287-289: (a // thr) [* min_threshold below]
       else if (SIMPLE || A.upd.mode == DVS_UPD_RATE) upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;  // gs:244-249
       else {  // time-binary updates gs:374-376 / gs:421-423: log2 table of abs_diff (raw) or of abs_diff // T
         const int idx = A.upd.mode == DVS_UPD_TIME_BIN_THR ? (int)__umulhi((unsigned)a, magic) : a;
@@ -355,11 +418,21 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
         ref_t[q] = (int16_t)clip(w16(r + u), 0, 255);
       } else ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
       int desc = 0;
-      if (SIMPLE) {
+      if (ENC == ENC_RATE_CODED) {
         tp = !neg; tn = neg;
         desc = max(0, (A.enc.n_slots - 1) - (int)__umulhi((unsigned)a, A.enc.dv.magic));  // k, gs:830-832
         if (desc == 0 && A.drop_silent) { tp = false; tn = false; }  // k == 0: in no slot; the record would only be skipped by K3
         else atomicAdd(&hist[(neg ? nh : 0) + desc], 1u);  // fire-and-forget shared-memory reduction (k <= n_slots - 1)
+      } else if (ENC == ENC_TIME_CODED) {
+        // make_spike_lists_time gs:903-926: one event in slot num_bins - min(v - 1, num_bins - 1) - 1, the neg list
+        // additionally clamps at 0 (gs:919-921); a pos spike with v == 0 lands outside the list of lists
+        tp = !neg; tn = neg;
+        const int v = (int)__umulhi((unsigned)a, A.enc.dv.magic);
+        int nt = min(v - 1, A.enc.n_slots - 1);
+        if (neg) nt = max(nt, 0);
+        desc = A.enc.n_slots - nt - 1;
+        if (desc >= A.enc.n_slots) { status |= DVS_STATUS_SLOT_RANGE; desc = -1; }
+        else atomicAdd(&hist[(neg ? nh : 0) + desc], 1u);
       } else {
         split_px(neg ? -1 : 1, A.polarity, A.uncoded, tp, tn);
         if (tp || tn) desc = hist_add(A, hist, nh, a, tp, hp, hn, status, /*allow_regs=*/false);
@@ -373,7 +446,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     w_neg += __popc(bn);
   }
   if (lane == 0) wtot[64 + warp] = w_pos | (w_neg << 16);
-  if (!SIMPLE) {  // only the status bits are left to publish: the histogram went straight to shared memory
+  if (ENC != ENC_RATE_CODED) {  // only the status bits are left to publish: the histogram went straight to shared memory
     status = __reduce_or_sync(kFull, status);
     if (status && lane == 0 && A.status) atomicOr(A.status, (int)status);
   }
@@ -397,10 +470,13 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   write_counters(A, s_idx, t_idx, hist, nh, n_pos_tile, n_neg_tile);
 }
 
-template <int SRC, int JH, bool PAIR, bool SIMPLE, bool ADAPT = false>
-__global__ void __launch_bounds__(256, ADAPT ? 4 : FAST2_MINB) k_tile_fast2(const __grid_constant__ TileArgs A) {
+#ifndef FAST2_MINB_ADPT
+#define FAST2_MINB_ADPT 4
+#endif
+template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT = false>
+__global__ void __launch_bounds__(256, ADAPT ? FAST2_MINB_ADPT : FAST2_MINB) k_tile_fast2(const __grid_constant__ TileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  fast2_tile<SRC, JH, PAIR, SIMPLE, ADAPT, false>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + kFastCap * 12,
+  fast2_tile<SRC, JH, PAIR, ENC, ADAPT, false>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + kFastCap * 12,
                                                   nullptr, nullptr);
 }
 
@@ -440,7 +516,7 @@ DEV void mbar_wait(uint64_t *bar, uint32_t parity) {
 #ifndef FAST2S_MINB
 #define FAST2S_MINB 3
 #endif
-template <int SRC, int JH, bool PAIR, bool SIMPLE>
+template <int SRC, int JH, bool PAIR, int ENC>
 __global__ void __launch_bounds__(256, FAST2S_MINB) k_tile_fast2s(const __grid_constant__ TileArgs A, const int stage_bytes) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char *ctl = smem_raw + 2 * stage_bytes;
@@ -479,14 +555,14 @@ __global__ void __launch_bounds__(256, FAST2S_MINB) k_tile_fast2s(const __grid_c
     mbar_wait(&bars[stage], (uint32_t)((k >> 1) & 1));
     const int s_idx = (int)(tile / A.tiles_per_stream), t_idx = (int)(tile - (long long)s_idx * A.tiles_per_stream);
     unsigned char *st = smem_raw + (size_t)stage * stage_bytes;
-    fast2_tile<SRC, JH, PAIR, SIMPLE, false, true>(A, t_idx, s_idx, st, ctl, st, st + cur_bytes_max);
+    fast2_tile<SRC, JH, PAIR, ENC, false, true>(A, t_idx, s_idx, st, ctl, st, st + cur_bytes_max);
     __syncthreads();  // tile k is finished with its stage, wtot and hist before anything of tile k + 1 touches them
   }
 }
 
-template <int SRC, int JH, bool PAIR, bool SIMPLE, bool ADAPT = false>
+template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT = false>
 static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
-  auto k = k_tile_fast2<SRC, JH, PAIR, SIMPLE, ADAPT>;
+  auto k = k_tile_fast2<SRC, JH, PAIR, ENC, ADAPT>;
   const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
   const size_t smem = kFastCap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t) + (ADAPT ? kFastCap * 2 : 0) + 256;
   cudaError_t e;
@@ -495,7 +571,7 @@ static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
   if ((e = cudaMemsetAsync(A.redo, 0, sizeof(int32_t), st)) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
   const long long tiles = (long long)A.S * A.tiles_per_stream;
   bool staged = false;
-  if constexpr (!ADAPT && PAIR) {
+  if constexpr (!ADAPT && PAIR && ENC != ENC_TIME_CODED) {
     // persistent staged kernel: worth it once every resident CTA has several tiles to walk
     const int stage_bytes = (A.tile_px * ((SRC == SRC_U8 ? 1 : 2) + 2) + 127) & ~127;
     const size_t smem_s = 2 * (size_t)stage_bytes + (((128 + 2 * nh + 8) * 4 + 256 + 15) & ~15) + 16;
@@ -507,7 +583,7 @@ static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
     }
     const long long resident = (long long)sm_count * FAST2S_MINB;
     if (A.use_staged == 2 && stage_bytes >= kFastCap * 12 && smem_s <= 72 * 1024) {  // opt-in: measured slower than one tile per CTA
-      auto ks = k_tile_fast2s<SRC, JH, PAIR, SIMPLE>;
+      auto ks = k_tile_fast2s<SRC, JH, PAIR, ENC>;
       if ((e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)) != cudaSuccess)
         return set_error((int)e, cudaGetErrorString(e));
       ks<<<(unsigned)resident, bd, smem_s, st>>>(A, stage_bytes);
@@ -530,47 +606,39 @@ static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
   return DVS_OK;
 }
 
-// Caller guarantees: vec_ok, W % 8 == 0, <= 1024 groups per tile, inhibition off or 2x2 on two-row tiles,
-// 2 <= T, rate or time-binary update, history_weight in [0, 1], max_time_ms >= 0, no debug planes.
-template <int SRC>
-static int dispatch_fast(const TileArgs &A, cudaStream_t st) {
+// Caller guarantees: vec_ok (incl. the threshold plane when ADAPT), W % 8 == 0, <= 1024 groups per tile, inhibition
+// off or 2x2 on two-row tiles; static: 2 <= T, rate or time-binary update, history_weight in [0, 1], max_time_ms >= 0;
+// adaptive: rate_adpt update, history_weight in [0, 1], 0 <= min <= max <= 32767, 0 <= up, down <= 32767; no debug planes.
+template <int SRC, bool ADAPT>
+static int dispatch_fast_shapes(const TileArgs &A, cudaStream_t st) {
   const int items = A.tile_px / 8;
-  // inlined membership / histogram: MERGED lists, coded RATE encoder, <= 8 slots, plain rate update
-  const bool simple = (A.uncoded == 0 && A.polarity == DVS_POL_MERGED) && A.enc.mode == DVS_ENC_RATE &&
-                      A.enc.uncoded == 0 && A.enc.n_slots <= 8 && A.enc.n_slots >= 1 && A.enc.threshold >= 2 &&
-                      A.enc.u16_vals == 0 && A.fast_hist && A.upd.mode == DVS_UPD_RATE && A.upd.hw_is_one;
+  // inlined membership / slot / histogram and index-only work list: MERGED lists of the coded module, coded RATE
+  // (<= 8 slots) or TIME encoder, plain rate update (rate_adpt when adaptive) without history decay
+  const bool coded = A.uncoded == 0 && A.polarity == DVS_POL_MERGED && A.enc.uncoded == 0 && A.enc.threshold >= 2 &&
+                     A.enc.u16_vals == 0 && A.upd.hw_is_one &&
+                     (ADAPT ? (A.upd.mode == DVS_UPD_RATE_ADPT && A.upd.uncoded == 0) : A.upd.mode == DVS_UPD_RATE);
+  int enc = ENC_ANY;
+  if (coded && A.enc.mode == DVS_ENC_RATE && A.enc.n_slots >= 1 && A.enc.n_slots <= 8 && A.fast_hist) enc = ENC_RATE_CODED;
+  else if (coded && A.enc.mode == DVS_ENC_TIME && A.enc.n_slots >= 1) enc = ENC_TIME_CODED;
   auto round32 = [](int x) { return (x + 31) / 32 * 32; };
+#define DVS_LAUNCH_ENC(JH_, PAIR_, BD_)                                                                      \
+  (enc == ENC_RATE_CODED   ? launch_fast2<SRC, JH_, PAIR_, ENC_RATE_CODED, ADAPT>(A, BD_, st)                 \
+   : enc == ENC_TIME_CODED ? launch_fast2<SRC, JH_, PAIR_, ENC_TIME_CODED, ADAPT>(A, BD_, st)                 \
+                           : launch_fast2<SRC, JH_, PAIR_, ENC_ANY, ADAPT>(A, BD_, st))
   if (A.inh_k != 2) {
-    if (items <= 256) {
-      const int bd = round32(items);
-      return simple ? launch_fast2<SRC, 1, false, true>(A, bd, st) : launch_fast2<SRC, 1, false, false>(A, bd, st);
-    }
-    const int bd = round32((items + 3) / 4);
-    return simple ? launch_fast2<SRC, 4, false, true>(A, bd, st) : launch_fast2<SRC, 4, false, false>(A, bd, st);
+    if (items <= 256) return DVS_LAUNCH_ENC(1, false, round32(items));
+    return DVS_LAUNCH_ENC(4, false, round32((items + 3) / 4));
   }
   const int gpr = A.W / 8;  // two-row tiles: each thread owns the same column block(s) in both rows
-  if (gpr <= 256) {
-    const int bd = round32(gpr);
-    return simple ? launch_fast2<SRC, 1, true, true>(A, bd, st) : launch_fast2<SRC, 1, true, false>(A, bd, st);
-  }
-  const int bd = round32((gpr + 1) / 2);
-  return simple ? launch_fast2<SRC, 2, true, true>(A, bd, st) : launch_fast2<SRC, 2, true, false>(A, bd, st);
+  if (gpr <= 256) return DVS_LAUNCH_ENC(1, true, round32(gpr));
+  return DVS_LAUNCH_ENC(2, true, round32((gpr + 1) / 2));
+#undef DVS_LAUNCH_ENC
 }
 
-// Adaptive-threshold fast path.  Caller guarantees: vec_ok (incl. the threshold plane), W % 8 == 0,
-// <= 1024 groups per tile, inhibition off or 2x2 on two-row tiles, coded rate_adpt update with
-// history_weight == 1, 0 <= min <= max <= 32767, 0 <= up, down <= 32767.
 template <int SRC>
-static int dispatch_fast_adpt(const TileArgs &A, cudaStream_t st) {
-  const int items = A.tile_px / 8;
-  auto round32 = [](int x) { return (x + 31) / 32 * 32; };
-  if (A.inh_k != 2) {
-    if (items <= 256) return launch_fast2<SRC, 1, false, false, true>(A, round32(items), st);
-    return launch_fast2<SRC, 4, false, false, true>(A, round32((items + 3) / 4), st);
-  }
-  const int gpr = A.W / 8;
-  if (gpr <= 256) return launch_fast2<SRC, 1, true, false, true>(A, round32(gpr), st);
-  return launch_fast2<SRC, 2, true, false, true>(A, round32((gpr + 1) / 2), st);
-}
+static int dispatch_fast(const TileArgs &A, cudaStream_t st) { return dispatch_fast_shapes<SRC, false>(A, st); }
+
+template <int SRC>
+static int dispatch_fast_adpt(const TileArgs &A, cudaStream_t st) { return dispatch_fast_shapes<SRC, true>(A, st); }
 
 }  // namespace dvs
