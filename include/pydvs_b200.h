@@ -156,6 +156,9 @@ typedef struct dvs_step_params {
 
 /* ---- library ---------------------------------------------------------------------------------- */
 int dvs_abi_version(void);
+/* Which tile kernel the calling thread's last dvs_step_fused launched (tests and benchmarks report it). */
+enum { DVS_PATH_GENERIC = 0, DVS_PATH_FAST = 1, DVS_PATH_FAST_4X4 = 2 };
+int dvs_last_step_path(void);
 const char *dvs_last_error_string(void);
 int dvs_get_limits(dvs_limits *out_host);
 /* Host helper: tile_rows for a geometry (multiple of max(inh_k,1), tile_rows*W <= max_tile_px). */

@@ -19,6 +19,7 @@ UPD_RATE, UPD_RATE_ADPT, UPD_TIME_BIN_RAW, UPD_TIME_BIN_THR, UPD_NONE = 0, 1, 2,
 ENC_RATE, ENC_TIME, ENC_TIME_BIN, ENC_TIME_BIN_THR, ENC_NONE = 0, 1, 2, 3, 4
 FRAME_I16, FRAME_U8 = 0, 1
 ABI_VERSION = 2
+PATH_GENERIC, PATH_FAST, PATH_FAST_4X4 = 0, 1, 2
 
 
 class Limits(C.Structure):
@@ -75,6 +76,7 @@ _P, _I32, _I64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 
 _SIGNATURES = {
     "dvs_abi_version": (C.c_int, []),
+    "dvs_last_step_path": (C.c_int, []),
     "dvs_last_error_string": (C.c_char_p, []),
     "dvs_get_limits": (C.c_int, [C.POINTER(Limits)]),
     "dvs_choose_tile_rows": (C.c_int, [_I32, _I32, _I32, _I32]),

@@ -783,6 +783,7 @@ __global__ void __launch_bounds__(256) k_move_mask(const int16_t *__restrict__ i
 using namespace dvs;
 
 static thread_local char g_err[512] = "";
+static thread_local int g_last_path = -1;  // which tile kernel the last dvs_step_fused of this thread launched
 
 static int fail(int code, const char *msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -831,6 +832,7 @@ static cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 extern "C" {
 
 int dvs_abi_version(void) { return DVS_ABI_VERSION; }
+int dvs_last_step_path(void) { return g_last_path; }
 const char *dvs_last_error_string(void) { return g_err; }
 
 int dvs_get_limits(dvs_limits *out) {
@@ -849,6 +851,7 @@ int dvs_choose_tile_rows(int32_t S, int32_t H, int32_t W, int32_t inh_k) {
   const int k = inh_k > 1 ? inh_k : 1;
   if (S <= 0 || H <= 0 || W <= 0 || (long long)W * k > kMaxTilePx) return -1;
   if (k == 2 && W % 8 == 0 && H % 2 == 0 && W >= 64) return 2;  // 2x2 areas stay inside one thread (k_tile_fast2)
+  if (k == 4 && W % 8 == 0 && H % 4 == 0 && W >= 64 && W <= 4096) return 4;  // 4x4 areas likewise (k_tile_fast4)
   const int target_px = 8192;
   int rows = (target_px / W) / k * k;
   if (rows < k) rows = k;
@@ -861,6 +864,13 @@ int dvs_choose_tile_rows(int32_t S, int32_t H, int32_t W, int32_t inh_k) {
     if (nr < k) nr = k;
     if (nr == rows) break;
     rows = nr;
+  }
+  if (k == 1 && W % 8 != 0) {
+    // rows that do not end on a 16-byte boundary: tiles of a multiple of 8 / gcd(W, 8) rows still start aligned, which
+    // is all the linear (no inhibition) fast kernel needs
+    const int g = (W % 4 == 0) ? 2 : (W % 2 == 0 ? 4 : 8);
+    if (rows >= g) rows = rows / g * g;
+    else if (H >= g && (long long)g * W <= kMaxTilePx) rows = g;
   }
   return rows;
 }
@@ -925,16 +935,28 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
   // fast path: static threshold, rate update, no history decay, vector-friendly geometry
   // (the register-only kernels also take 0 <= history_weight < 1 and the time-binary updates)
   const bool plain = p->update_mode == DVS_UPD_RATE && p->history_weight == 1.0;
-  const bool regs_only = k == 1 || (k == 2 && A.tile_rows == 2 && A.H % 2 == 0);
+  // 4x4 inhibition in registers: four-row tiles, one column block per thread (<= 512 threads) and an inlined encoder
+  const bool coded_lists = p->uncoded == 0 && p->polarity == DVS_POL_MERGED && p->enc.uncoded == 0 && p->enc.threshold >= 2 &&
+                           p->enc.u16_vals == 0 && p->history_weight == 1.0 &&
+                           ((p->enc.mode == DVS_ENC_RATE && p->enc.n_slots >= 1 && p->enc.n_slots <= 8) ||
+                            (p->enc.mode == DVS_ENC_TIME && p->enc.n_slots >= 1));
+  const bool quad = k == 4 && A.tile_rows == 4 && A.H % 4 == 0 && A.W % 8 == 0 && A.W / 8 <= 512 && coded_lists &&
+                    (p->adaptive ? p->update_mode == DVS_UPD_RATE_ADPT : p->update_mode == DVS_UPD_RATE);
+  const int max_groups = quad ? 2048 : 1024;
+  const bool regs_only = k == 1 || (k == 2 && A.tile_rows == 2 && A.H % 2 == 0 && A.W % 8 == 0) || quad;
   const bool upd_ok = regs_only && (plain || (p->history_weight >= 0.0 && p->history_weight <= 1.0 &&
                                              (p->update_mode == DVS_UPD_RATE || p->update_mode == DVS_UPD_TIME_BIN_RAW ||
                                               (p->update_mode == DVS_UPD_TIME_BIN_THR && p->threshold <= 128))));
   const bool fast = !p->adaptive && upd_ok &&
                     p->threshold >= 2 && p->threshold <= 32767 && p->max_time_ms >= 0 && A.vec_ok &&
-                    A.W % 8 == 0 && A.tile_px / 8 <= 1024 && !p->diff_out && !p->abs_diff_out &&
+                    A.tile_px / 8 <= max_groups && !p->diff_out && !p->abs_diff_out &&
                     !p->spikes_out && p->force_generic != 1 && p->redo && A.S <= 65535;
   A.redo = p->redo;
-  if (fast) return u8 ? launch_tile_fast_u8(A, st) : launch_tile_fast_i16(A, st);
+  g_last_path = DVS_PATH_GENERIC;
+  if (fast) {
+    g_last_path = quad ? DVS_PATH_FAST_4X4 : DVS_PATH_FAST;
+    return u8 ? launch_tile_fast_u8(A, st) : launch_tile_fast_i16(A, st);
+  }
   // adaptive fast path: coded rate_adpt rule, no history decay, inhibition off or 2x2 on two-row tiles
   // (uncoded rule: th - down must not borrow below zero lane-wise, so thresholds start and stay >= down is not
   //  guaranteed -> require min_thr >= 0 and let the range vote catch negative planes; th > min >= 0 => th - down
@@ -943,10 +965,13 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
   const bool fast_adpt = p->adaptive && p->update_mode == DVS_UPD_RATE_ADPT && unc_ok &&
                          p->history_weight >= 0.0 && p->history_weight <= 1.0 &&
                          p->min_thr >= 0 && p->min_thr <= p->max_thr && p->max_thr <= 32767 && p->thr_up >= 0 &&
-                         p->thr_up <= 32767 && p->thr_down >= 0 && p->thr_down <= 32767 && A.vec_ok && A.W % 8 == 0 &&
-                         A.tile_px / 8 <= 1024 && (k == 1 || (k == 2 && A.tile_rows == 2 && A.H % 2 == 0)) &&
+                         p->thr_up <= 32767 && p->thr_down >= 0 && p->thr_down <= 32767 && A.vec_ok &&
+                         A.tile_px / 8 <= max_groups && regs_only &&
                          !p->diff_out && !p->abs_diff_out && !p->spikes_out && p->force_generic != 1 && p->redo && A.S <= 65535;
-  if (fast_adpt) return u8 ? launch_tile_fast_u8_adpt(A, st) : launch_tile_fast_i16_adpt(A, st);
+  if (fast_adpt) {
+    g_last_path = quad ? DVS_PATH_FAST_4X4 : DVS_PATH_FAST;
+    return u8 ? launch_tile_fast_u8_adpt(A, st) : launch_tile_fast_i16_adpt(A, st);
+  }
   if (u8) return p->adaptive ? launch_tile_pass_u8_adpt(A, st) : launch_tile_pass_u8(A, st);
   return p->adaptive ? launch_tile_pass_i16_adpt(A, st) : launch_tile_pass_i16(A, st);
 }

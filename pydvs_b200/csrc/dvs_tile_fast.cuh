@@ -54,11 +54,23 @@ enum { ENC_ANY = 0, ENC_RATE_CODED = 1, ENC_TIME_CODED = 2 };
 DEV int adpt_div(int a, int thr) {
   return thr == 0 ? 0 : (int)(((float)a + 0.5f) * __frcp_rn((float)thr));
 }
-template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT, bool STAGED>
+// QUAD: 4x4 inhibition on four-row tiles -- the PAIR mapping with four rows per column block (JH == 1): a thread holds
+// two complete 4x4 areas (columns 0-3 and 4-7 of its block) in registers, the arg-max is a packed maximum over keys
+// abs_diff * 16 + (15 - index in the area), and the winners go to the index-only work list (ENC != 0).  Rows of up to
+// 4096 pixels: CTAs of up to 512 threads.
+template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT, bool STAGED, bool QUAD = false>
 DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigned char *smem_raw, unsigned char *ctl,
                     const unsigned char *st_cur, const unsigned char *st_ref) {
-  constexpr int J = PAIR ? 2 * JH : JH;
+  static_assert(!QUAD || (PAIR && JH == 1 && ENC != ENC_ANY && !STAGED), "4x4 variant: one column block, inlined encoders");
+  constexpr int J = QUAD ? 4 : (PAIR ? 2 * JH : JH);
   constexpr bool SIMPLE = ENC != ENC_ANY;
+  // index-only work list (see above), K1 ms at 64 streams with / without it (gpurun sweep, round 2): uint8 4K frames
+  // 0.503 / 0.581, 4K without inhibition 0.598 / 0.625 -- but int16 dense 4K 1.204 / 1.142 (the static 2x2 area walk does
+  // not diverge) and adaptive 1080p 0.321 / 0.309 (the old threshold has to be extracted for the entry anyway)
+#ifndef FAST2_QONLY_MODE
+#define FAST2_QONLY_MODE 2
+#endif
+  constexpr bool QONLY = QUAD || (SIMPLE && (FAST2_QONLY_MODE == 1 || (FAST2_QONLY_MODE == 2 && !ADAPT && (!PAIR || SRC == SRC_U8))));
   uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
   uint16_t *wl16 = reinterpret_cast<uint16_t *>(smem_raw);  // ENC != 0: pixel indices only
   uint2 *rec_sm = reinterpret_cast<uint2 *>(smem_raw + kFastCap * 4);
@@ -165,7 +177,35 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     const uint32_t over = A.upd.uncoded ? tmax : (tmax | (tmax + (uint32_t)A.upd.thr_up * 0x00010001u));
     if (over & 0x80008000u) rng |= 0xFF00u;
   }
-  if (PAIR) {
+  if (QUAD) {
+    // local_inhibition gs:177-221 for 4x4 areas on registers.  Group j is row j of the tile; words 0-1 / 2-3 of the four
+    // groups form the left / right area of the column block.  argmax gs:118-132 keeps the FIRST maximum in row-major
+    // order: with keys a * 16 + (15 - index) a plain maximum does that (a <= 255, so a key fits a 16-bit lane).
+    if ((flags8[0] | flags8[1]) | (flags8[2] | flags8[3])) {
+      uint32_t keep[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int sd = 0; sd < 2; ++sd) {
+        uint32_t best = 0u;
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+          if (flags8[r4] == 0) continue;   // no spike in this row of the block: its masked abs_diff is zero
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const uint32_t idx_lo = 15u - (4u * r4 + 2u * h2), idx_hi = idx_lo - 1u;
+            best = __vmaxu2(best, masked_abs(r4, 2 * sd + h2) * 16u + (idx_lo | (idx_hi << 16)));
+          }
+        }
+        const uint32_t m = max(best & 0xffffu, best >> 16);
+        if ((m >> 4) != 0u) {  // some pixel of the area spikes: only the winner keeps its spike
+          const uint32_t idx = 15u - (m & 15u), row = idx >> 2, bit = 1u << (4 * sd + (idx & 3u));
+#pragma unroll
+          for (int r4 = 0; r4 < 4; ++r4) keep[r4] |= row == (uint32_t)r4 ? bit : 0u;
+        }
+      }
+#pragma unroll
+      for (int r4 = 0; r4 < 4; ++r4) flags8[r4] = keep[r4];
+    }
+  } else if (PAIR) {
     // local_inhibition gs:177-221 on registers: of each 2x2 area (word w of the upper and of the lower
     // row group) only the first arg-max of abs_diff * spikes keeps its spike (row-major, strict '>')
 #pragma unroll
@@ -195,6 +235,25 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     const uint32_t up2 = (uint32_t)A.upd.thr_up * 0x00010001u, dn2 = (uint32_t)A.upd.thr_down * 0x00010001u;
     const uint32_t mn2 = (uint32_t)A.upd.min_thr * 0x00010001u, mx2 = (uint32_t)A.upd.max_thr * 0x00010001u;
     const uint32_t mnd2 = mn2 + dn2;
+    if (!A.upd.uncoded && A.upd.thr_up + A.upd.thr_down <= 32768) {
+      // coded rule in a domain biased by `down` (no lane can borrow): x = th + (spike ? up + down : 0) stands for
+      // th + up resp. th - down, clip(x, min + down, max + down) - down is the clipped threshold.  th + up <= 32767
+      // (range vote) and up + down <= 32768 keep every lane below 2^16.  The 2-bit spike field of a word becomes a lane
+      // mask with two multiplications: ((f >> 2w) * 0x8001) & 0x10001 moves the bits to positions 0 and 16.
+      const uint32_t ud2 = up2 + dn2, mxd2 = mx2 + dn2;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        if (!have[j]) continue;
+        uint32_t tn[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t m = (((flags8[j] >> (2 * w)) * 0x8001u) & 0x10001u) * 0xffffu;
+          tn[w] = __vminu2(__vmaxu2(t_pk[j][w] + (m & ud2), mnd2), mxd2) - dn2;
+        }
+        st16(thr_t + q0_of(j), tn);
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       if (!have[j]) continue;
@@ -261,9 +320,11 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   }
   __syncthreads();
   const uint32_t ent_raw = lane < J * NW ? wtot[lane] : 0u;  // every warp reads the <= 32 totals
-  const bool unsafe = __any_sync(kFull, (ent_raw >> 31) != 0u);
-  const uint32_t ent = ent_raw & 0x7fffffffu;
-  const int n_cand = (int)__reduce_add_sync(kFull, ent);  // redux.sync: the tile's candidate count
+  // QUAD: up to 16 warps x 4 rows = 64 (row, warp) totals, two per lane
+  const uint32_t ent_raw2 = (QUAD && lane + 32 < J * NW) ? wtot[lane + 32] : 0u;
+  const bool unsafe = __any_sync(kFull, ((ent_raw | ent_raw2) >> 31) != 0u);
+  const uint32_t ent = ent_raw & 0x7fffffffu, ent2 = ent_raw2 & 0x7fffffffu;
+  const int n_cand = (int)__reduce_add_sync(kFull, ent + ent2);  // redux.sync: the tile's candidate count
   if (n_cand == 0 && !unsafe) {  // quiet tile: no records, no events, reference untouched (unless it decays)
     if (ADAPT) store_thresholds();
     if (decay) store_decayed_reference();
@@ -288,9 +349,9 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     uint32_t pos_of[J];
 #pragma unroll
     for (int j = 0; j < J; ++j)
-      pos_of[j] = __reduce_add_sync(kFull, lane < j * NW + warp ? ent : 0u) +  // candidates of earlier (group, warp) pairs
-                  (((j < 2 ? ex_lo : ex_hi) >> (16 * (j & 1))) & 0xffffu);
-    if (SIMPLE && PAIR) {
+      pos_of[j] = __reduce_add_sync(kFull, (lane < j * NW + warp ? ent : 0u) + (lane + 32 < j * NW + warp ? ent2 : 0u)) +
+                  (((j < 2 ? ex_lo : ex_hi) >> (16 * (j & 1))) & 0xffffu);  // + candidates of earlier (group, warp) pairs
+    if (QONLY && PAIR && !QUAD) {
       // index-only entries: one 16-bit store per surviving area
 #pragma unroll
       for (int h = 0; h < JH; ++h) {
@@ -309,7 +370,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
           if (up) pos_of[ju] = pos + 1; else pos_of[jl] = pos + 1;
         }
       }
-    } else if (SIMPLE) {
+    } else if (QONLY) {
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         if (flags8[j] == 0) continue;
@@ -389,7 +450,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     if (i < hi) {
       int q, r, a;
       bool neg;
-      if (SIMPLE) {  // index-only entry: fetch the pixel again (both values are in [0, 255]: the tile passed the range vote)
+      if (QONLY) {  // index-only entry: fetch the pixel again (both values are in [0, 255]: the tile passed the range vote)
         q = wl16[i];
         // the tile's frame pointer is rebuilt from the reference pointer (kernel parameters are free, live registers are not)
         const long long boff = reinterpret_cast<const char *>(ref_t) - reinterpret_cast<const char *>(A.ref);
@@ -478,6 +539,14 @@ __global__ void __launch_bounds__(256, ADAPT ? FAST2_MINB_ADPT : FAST2_MINB) k_t
   extern __shared__ __align__(16) unsigned char smem_raw[];
   fast2_tile<SRC, JH, PAIR, ENC, ADAPT, false>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + kFastCap * 12,
                                                   nullptr, nullptr);
+}
+
+// 4x4 inhibition: one column block per thread over four rows; MAXT = 256 (rows up to 2048 px) or 512 (up to 4096 px)
+template <int SRC, int ENC, bool ADAPT, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 256 ? 4 : 2) k_tile_fast4(const __grid_constant__ TileArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  fast2_tile<SRC, 1, true, ENC, ADAPT, false, true>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + kFastCap * 12,
+                                                     nullptr, nullptr);
 }
 
 // ---- persistent, staged variant (opt-in: dvs_step_params.force_generic == 3) -----------------------
@@ -606,6 +675,38 @@ static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
   return DVS_OK;
 }
 
+template <int SRC, int ENC, bool ADAPT>
+static int launch_fast4(const TileArgs &A, cudaStream_t st) {
+  const int nh = A.enc.n_slots + 1;
+  const size_t smem = kFastCap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t) + (ADAPT ? kFastCap * 2 : 0) + 256;
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(A.redo, 0, sizeof(int32_t), st)) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+  const int gpr = A.W / 8, bd = (gpr + 31) / 32 * 32;
+  const dim3 grid((unsigned)A.tiles_per_stream, (unsigned)A.S);
+  if (bd <= 256) {
+    auto k = k_tile_fast4<SRC, ENC, ADAPT, 256>;
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+      return set_error((int)e, cudaGetErrorString(e));
+    k<<<grid, bd, smem, st>>>(A);
+  } else {
+    auto k = k_tile_fast4<SRC, ENC, ADAPT, 512>;
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+      return set_error((int)e, cudaGetErrorString(e));
+    k<<<grid, bd, smem, st>>>(A);
+  }
+  if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+  // generic body (shared-memory plane, any inhibition width) over the declined tiles
+  auto kr = k_tile_redo<SRC, 4, INH_GENERIC, ADAPT, 1024>;
+  const size_t smem_r = ((A.tile_px * 2 + 15) & ~15) + (128 + 2 * nh + 8) * sizeof(uint32_t);
+  if (smem_r > 48 * 1024 && (e = cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)) != cudaSuccess)
+    return set_error((int)e, cudaGetErrorString(e));
+  const int items = A.tile_px / 8;
+  const long long tiles = (long long)A.S * A.tiles_per_stream;
+  kr<<<(unsigned)(tiles < 296 ? tiles : 296), ((items + 3) / 4 + 31) / 32 * 32, smem_r, st>>>(A);
+  if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+  return DVS_OK;
+}
+
 // Caller guarantees: vec_ok (incl. the threshold plane when ADAPT), W % 8 == 0, <= 1024 groups per tile, inhibition
 // off or 2x2 on two-row tiles; static: 2 <= T, rate or time-binary update, history_weight in [0, 1], max_time_ms >= 0;
 // adaptive: rate_adpt update, history_weight in [0, 1], 0 <= min <= max <= 32767, 0 <= up, down <= 32767; no debug planes.
@@ -621,6 +722,11 @@ static int dispatch_fast_shapes(const TileArgs &A, cudaStream_t st) {
   if (coded && A.enc.mode == DVS_ENC_RATE && A.enc.n_slots >= 1 && A.enc.n_slots <= 8 && A.fast_hist) enc = ENC_RATE_CODED;
   else if (coded && A.enc.mode == DVS_ENC_TIME && A.enc.n_slots >= 1) enc = ENC_TIME_CODED;
   auto round32 = [](int x) { return (x + 31) / 32 * 32; };
+  if (A.inh_k == 4) {  // caller: four-row tiles, W <= 4096, enc != ENC_ANY (dvs_step_fused checks fast4_ok())
+    if (enc == ENC_RATE_CODED) return launch_fast4<SRC, ENC_RATE_CODED, ADAPT>(A, st);
+    if (enc == ENC_TIME_CODED) return launch_fast4<SRC, ENC_TIME_CODED, ADAPT>(A, st);
+    return set_error(DVS_ERR_UNSUPPORTED, "internal: 4x4 fast path needs an inlined encoder");
+  }
 #define DVS_LAUNCH_ENC(JH_, PAIR_, BD_)                                                                      \
   (enc == ENC_RATE_CODED   ? launch_fast2<SRC, JH_, PAIR_, ENC_RATE_CODED, ADAPT>(A, BD_, st)                 \
    : enc == ENC_TIME_CODED ? launch_fast2<SRC, JH_, PAIR_, ENC_TIME_CODED, ADAPT>(A, BD_, st)                 \

@@ -425,8 +425,8 @@ __global__ void __launch_bounds__(BDMAX) k_tile_pass(const __grid_constant__ Til
 
 // Generic body over the tiles the fast kernel declined (pixels outside [0, 255]): A.redo[0] = count,
 // A.redo[1..] = tile indices.  Launched after every fast pass; normally finds count == 0.
-template <int SRC, int J, int KI, bool ADAPT = false>
-__global__ void __launch_bounds__(256) k_tile_redo(const __grid_constant__ TileArgs A) {
+template <int SRC, int J, int KI, bool ADAPT = false, int BDMAX = 256>
+__global__ void __launch_bounds__(BDMAX) k_tile_redo(const __grid_constant__ TileArgs A) {
   const int n = A.redo[0];
   for (int i = blockIdx.x; i < n; i += gridDim.x) {
     tile_body<SRC, J, ADAPT, KI>(A, A.redo[1 + i]);

@@ -379,6 +379,7 @@ class DVSStreams:
         self._params.curr = frames.data_ptr()
         self._params.records, self._params.tile_counts = self.records.data_ptr(), self.tile_counts.data_ptr()
         check(lib.dvs_step_fused(C.byref(self._params), current_stream_ptr()))
+        self.kernel_path = lib.dvs_last_step_path()   # _lib.PATH_*: which tile kernel ran (generic body or a fast path)
 
     def scan(self):
         """K2: per-tile counters -> exclusive prefixes and CSR row pointers (two small launches)."""

@@ -298,6 +298,34 @@ def test_fast_adaptive_kernel_declines_out_of_range_tiles():
     _run_case(1, 8, 1920, output_type="RATE", adaptive=True, inh=2, source="wide", frames=3, thr0=12, debug=False)
 
 
+def test_fast_kernel_4x4_inhibition():
+    # k = 4 in registers (k_tile_fast4): four-row tiles, a thread owns two 4x4 areas of its column block
+    from pydvs_b200 import _lib
+    for kw in (dict(S=2, H=16, W=64), dict(S=2, H=8, W=1920, source="bar"), dict(S=1, H=8, W=3840),       # 480 threads
+               dict(S=2, H=16, W=256, output_type="TIME", num_bins=8), dict(S=2, H=16, W=128, frame_dtype="uint8"),
+               dict(S=2, H=8, W=1920, adaptive=True, thr0=12, output_type="TIME", num_bins=4, max_time_ms=4, source="bar"),
+               dict(S=2, H=16, W=512, adaptive=True, thr0=12), dict(S=1, H=12, W=72, source="narrow")):
+        kw = dict(kw)
+        S, H, W = kw.pop("S"), kw.pop("H"), kw.pop("W")
+        dvs = _run_case(S, H, W, inh=4, frames=5, debug=False, **kw)
+        assert dvs.kernel_path == _lib.PATH_FAST_4X4, kw
+    # outside [0, 255]: declined tiles go through the generic body; generic encoders keep the generic kernel
+    assert _run_case(2, 16, 256, inh=4, source="wide", frames=3, debug=False).kernel_path == _lib.PATH_FAST_4X4
+    assert _run_case(2, 16, 64, inh=4, output_type="TIME_BIN", num_bins=8, lut_bits=(3, 8), threshold=5, source="narrow",
+                     frames=3, debug=False).kernel_path == _lib.PATH_GENERIC
+
+
+def test_fast_kernel_rows_that_are_not_a_multiple_of_eight_pixels():
+    # inhibition off: the linear fast kernel only needs tiles (not rows) to start on 16-byte boundaries
+    from pydvs_b200 import _lib
+    for (S, H, W) in ((2, 16, 36), (2, 24, 346), (1, 16, 641), (3, 8, 100)):
+        dvs = _run_case(S, H, W, frames=5, debug=False, source="bar")
+        assert dvs.kernel_path == _lib.PATH_FAST, (H, W, dvs.tile_rows)
+        dvs = _run_case(S, H, W, frames=4, debug=False, adaptive=True, thr0=12, output_type="TIME", num_bins=4, max_time_ms=4)
+        assert dvs.kernel_path == _lib.PATH_FAST, (H, W)
+    assert _run_case(1, 9, 13, frames=3, debug=False).kernel_path == _lib.PATH_GENERIC     # 117 pixels: not even 8-px planes
+
+
 def test_fast_adaptive_kernel_int16_wrap_boundaries():
     # gs:289-297 in int16: th + up above 32767 wraps negative and clips to min (not max); (a // th) * min_threshold wraps
     # for a caller-supplied plane below min_threshold.  Fast kernel and generic body must both follow the oracle.
