@@ -44,6 +44,10 @@ WORKLOADS = {
                                   num_bins=None, hw=1.0, ref0=128),
     "4k_rate_no_inhibition": dict(W=3840, H=2160, S=256, output_type="RATE", inh=0, adaptive=False, max_time_ms=8,
                                   num_bins=None, hw=1.0, ref0=128),
+    "4k_rate_inhibition_4x4": dict(W=3840, H=2160, S=256, output_type="RATE", inh=4, adaptive=False, max_time_ms=8,
+                                   num_bins=None, hw=1.0, ref0=128),
+    "davis346_rate": dict(W=346, H=260, S=1024, output_type="RATE", inh=0, adaptive=False, max_time_ms=8, num_bins=None,
+                          hw=1.0, ref0=128),
     "1080p_time_adaptive": dict(W=1920, H=1080, S=64, output_type="TIME", inh=0, adaptive=True, max_time_ms=4,
                                 num_bins=4, hw=1.0, ref0=128),
     "vga_rate_inhibition": dict(W=640, H=480, S=1, output_type="RATE", inh=2, adaptive=False, max_time_ms=8,
@@ -92,7 +96,8 @@ def parse_args():
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--no-weak-leg", action="store_true", help="N > 1: skip the secondary weak-scaling measurement")
     ap.add_argument("--pipeline-depth", type=int, default=1, choices=[1, 2])
-    ap.add_argument("--k1-variant", default="auto", choices=["auto", "plain", "staged"])
+    ap.add_argument("--k1-variant", default="auto", choices=["auto", "plain", "staged", "generic"],
+                    help="generic: force the generic tile body (what shapes outside the fast paths run)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="CUDA-graph replay of the step (auto: DVSStreams decides by problem size)")
     ap.add_argument("--settle", type=int, default=24,
@@ -431,7 +436,7 @@ class Case:
                         threshold0=12 if wl["adaptive"] else None, ref0=wl["ref0"])
         g = {"auto": "auto", "on": True, "off": False}[graph]
         self.dvs = DVSStreams(cfg, device=device, event_capacity=1 << 16, pipeline_depth=pipeline_depth,
-                              force_generic={"auto": 0, "plain": 0, "staged": 3}[k1_variant],
+                              force_generic={"auto": 0, "plain": 0, "staged": 3, "generic": 1}[k1_variant],
                               split_lists=False, graph=g)   # AER events are the output; split_spikes lists are not requested
         self.ring = ring if ring is not None else make_ring(wl, S, ring_n, pattern, frame_dtype, device, stream_base)
         self.i = 0

@@ -961,7 +961,7 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
   // (uncoded rule: th - down must not borrow below zero lane-wise, so thresholds start and stay >= down is not
   //  guaranteed -> require min_thr >= 0 and let the range vote catch negative planes; th > min >= 0 => th - down
   //  can go negative only if down > th - 0, which the generic body handles: restrict to down <= min_thr + 1)
-  const bool unc_ok = !p->uncoded || (p->thr_down <= p->min_thr + 1);
+  const bool unc_ok = p->uncoded ? (p->thr_down <= p->min_thr + 1) : ((long long)p->thr_up + p->thr_down <= 32768);
   const bool fast_adpt = p->adaptive && p->update_mode == DVS_UPD_RATE_ADPT && unc_ok &&
                          p->history_weight >= 0.0 && p->history_weight <= 1.0 &&
                          p->min_thr >= 0 && p->min_thr <= p->max_thr && p->max_thr <= 32767 && p->thr_up >= 0 &&

@@ -26,6 +26,14 @@ DEV uint4 ld16_stream(const void *p) { return __ldcs(reinterpret_cast<const uint
 #ifndef FAST2_MINB
 #define FAST2_MINB 5
 #endif
+// tuning switches (tools/build_variant.py builds the alternatives; the defaults are the measured winners)
+#ifndef FAST2_THR_BIASED
+#define FAST2_THR_BIASED 2   // coded threshold update in the `down`-biased domain (one clip) instead of two clips + select:
+                             // 0 never, 1 always, 2 uint8 frames only (K1 ms, 64 x 1080p: int16 0.308 / 0.319, uint8 0.329 / 0.318)
+#endif
+#ifndef FAST2_QONLY_ADAPT
+#define FAST2_QONLY_ADAPT 0  // index-only work list for the adaptive kernels as well
+#endif
 constexpr int kFastCap = 2048;  // work-list capacity; denser tiles go to the generic body (redo list)
 
 // ---- fast kernel, register-only variant ---------------------------------------------------------
@@ -70,7 +78,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
 #ifndef FAST2_QONLY_MODE
 #define FAST2_QONLY_MODE 2
 #endif
-  constexpr bool QONLY = QUAD || (SIMPLE && (FAST2_QONLY_MODE == 1 || (FAST2_QONLY_MODE == 2 && !ADAPT && (!PAIR || SRC == SRC_U8))));
+  constexpr bool QONLY = QUAD || (SIMPLE && (FAST2_QONLY_MODE == 1 || (FAST2_QONLY_MODE == 2 && (ADAPT ? FAST2_QONLY_ADAPT != 0 : (!PAIR || SRC == SRC_U8)))));
   uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
   uint16_t *wl16 = reinterpret_cast<uint16_t *>(smem_raw);  // ENC != 0: pixel indices only
   uint2 *rec_sm = reinterpret_cast<uint2 *>(smem_raw + kFastCap * 4);
@@ -235,7 +243,8 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     const uint32_t up2 = (uint32_t)A.upd.thr_up * 0x00010001u, dn2 = (uint32_t)A.upd.thr_down * 0x00010001u;
     const uint32_t mn2 = (uint32_t)A.upd.min_thr * 0x00010001u, mx2 = (uint32_t)A.upd.max_thr * 0x00010001u;
     const uint32_t mnd2 = mn2 + dn2;
-    if (!A.upd.uncoded && A.upd.thr_up + A.upd.thr_down <= 32768) {
+    constexpr bool BIASED = FAST2_THR_BIASED == 1 || (FAST2_THR_BIASED == 2 && SRC == SRC_U8);
+    if (BIASED && !A.upd.uncoded) {  // (the host admits the coded rule only with up + down <= 32768)
       // coded rule in a domain biased by `down` (no lane can borrow): x = th + (spike ? up + down : 0) stands for
       // th + up resp. th - down, clip(x, min + down, max + down) - down is the clipped threshold.  th + up <= 32767
       // (range vote) and up + down <= 32768 keep every lane below 2^16.  The 2-bit spike field of a word becomes a lane
@@ -262,7 +271,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       for (int w = 0; w < 4; ++w) {
         const uint32_t th = t_pk[j][w];
         uint32_t t_dn, t_up = 0;
-        if (!A.upd.uncoded) {
+        if (!BIASED && !A.upd.uncoded) {
           t_dn = __vminu2(__vmaxu2(th, mnd2) - dn2, mx2);                // clip(th - down, min, max)
           if (flags8[j]) t_up = __vminu2(__vmaxu2(th + up2, mn2), mx2);  // clip(th + up, min, max); th + up <= 32767 (range vote)
         } else {

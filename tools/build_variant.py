@@ -37,6 +37,8 @@ def main():
                        capture_output=True, text=True)
     if r.returncode:
         raise RuntimeError(r.stderr)
+    import shutil
+    shutil.rmtree(obj_dir, ignore_errors=True)   # objects are large (-lineinfo) and everything under the repo travels to the GPU box
     print("built", out)
 
 
