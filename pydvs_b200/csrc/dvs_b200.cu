@@ -96,17 +96,27 @@ __global__ void __launch_bounds__(256) k_scan_tiles(int n_rows, int tps, const u
   if (gw >= n_rows) return;
   const size_t base = (size_t)gw * tps;
   uint32_t carry = 0;
-  for (int t0 = 0; t0 < tps; t0 += 32) {
-    const int t = t0 + lane;
-    const uint32_t v = t < tps ? counts[base + t] : 0;
-    uint32_t x = v;
+  // 256 tiles per pass: the eight loads of a lane are independent and in flight together (a warp walking its row 32
+  // tiles at a time pays one DRAM / L2 latency per step of the carry chain: 34 of them for a 4K stream)
+  for (int t0 = 0; t0 < tps; t0 += 256) {
+    uint32_t v[8];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(kFull, x, o);
-      if (lane >= o) x += y;
+    for (int u = 0; u < 8; ++u) {
+      const int t = t0 + u * 32 + lane;
+      v[u] = t < tps ? counts[base + t] : 0;
     }
-    if (t < tps) excl[base + t] = carry + x - v;
-    carry += __shfl_sync(kFull, x, 31);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int t = t0 + u * 32 + lane;
+      uint32_t x = v[u];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(kFull, x, o);
+        if (lane >= o) x += y;
+      }
+      if (t < tps) excl[base + t] = carry + x - v[u];
+      carry += __shfl_sync(kFull, x, 31);
+    }
   }
   if (lane == 0) totals[gw] = carry;
 }

@@ -167,7 +167,7 @@ class StepResult:
 
 class DVSStreams:
     # below this many pixels per step (all streams) a step is launch-bound and is replayed as a CUDA graph
-    AUTO_GRAPH_MAX_PX = 1 << 26
+    AUTO_GRAPH_MAX_PX = 1 << 28
     GRAPH_CACHE = 16          # distinct frame buffers (by address) that get their own captured graph
 
     def __init__(self, cfg: DVSConfig, device=None, event_capacity: Optional[int] = None,
