@@ -31,6 +31,13 @@ DEV uint4 ld16_stream(const void *p) { return __ldcs(reinterpret_cast<const uint
 #define FAST2_THR_BIASED 2   // coded threshold update in the `down`-biased domain (one clip) instead of two clips + select:
                              // 0 never, 1 always, 2 uint8 frames only (K1 ms, 64 x 1080p: int16 0.308 / 0.319, uint8 0.329 / 0.318)
 #endif
+#ifndef FAST2_INH_KEYS
+#define FAST2_INH_KEYS 1     // 2x2 arg-max through packed keys instead of a compare / select chain (int16 frames; with
+                             // uint8 frames both switches cost 10 %: K1 0.557 vs 0.504 ms at 64 x 4K)
+#endif
+#ifndef FAST2_PAIR_XY
+#define FAST2_PAIR_XY 1      // two-row tiles: row / column of a candidate by one compare instead of a multiply-high
+#endif
 #ifndef FAST2_QONLY_ADAPT
 #define FAST2_QONLY_ADAPT 0  // index-only work list for the adaptive kernels as well
 #endif
@@ -224,6 +231,16 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         const uint32_t up = flags8[ju] ? masked_abs(ju, w) : 0u, lo = flags8[jl] ? masked_abs(jl, w) : 0u;
+        if (FAST2_INH_KEYS && SRC == SRC_I16) {
+        // keys abs_diff * 4 + (3 - index in the area): the maximum key is the FIRST maximum in row-major order
+        // (abs_diff <= 255 on this path, so a key fits its 16-bit lane)
+        const uint32_t m2 = __vmaxu2(up * 4u + 0x00020003u, lo * 4u + 0x00000001u);
+        const uint32_t m = max(m2 & 0xffffu, m2 >> 16);
+        if (m >> 2) {
+          const uint32_t bi = 3u - (m & 3u);
+          if (bi < 2) ku |= 1u << (2 * w + bi); else kl |= 1u << (2 * w + bi - 2);
+        }
+        } else {
         const int t00 = up & 0xffff, t01 = up >> 16, t10 = lo & 0xffff, t11 = lo >> 16;
         int best = t00, bi = 0;
         if (t01 > best) { best = t01; bi = 1; }
@@ -231,6 +248,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
         if (t11 > best) { best = t11; bi = 3; }
         if (best > 0) {
           if (bi < 2) ku |= 1u << (2 * w + bi); else kl |= 1u << (2 * w + bi - 2);
+        }
         }
       }
       flags8[ju] = ku; flags8[jl] = kl;
@@ -473,7 +491,9 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
         q = e & 0x1fff; r = (e >> 13) & 0xff; a = (e >> 21) & 0xff;
         neg = (e >> 29) & 1u;
       }
-      const int y = (int)__umulhi((unsigned)q, A.inv_w), x = q - y * A.W;
+      int y, x;
+      if (FAST2_PAIR_XY && SRC == SRC_I16 && PAIR && !QUAD) { y = q >= A.W ? 1 : 0; x = q - (y ? A.W : 0); }  // two-row tiles
+      else { y = (int)__umulhi((unsigned)q, A.inv_w); x = q - y * A.W; }
       int upd;
       if (ADAPT) upd = SIMPLE ? adpt_div(a, (int)wl_thr[i]) : np_floordiv(a, (int)wl_thr[i]);  // gs:287-289: (a // thr) [* min_threshold below]
       else if (SIMPLE || A.upd.mode == DVS_UPD_RATE) upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;  // gs:244-249
