@@ -7,6 +7,15 @@ rep = sys.argv[1]
 phases = []
 for a in sys.argv[2:]:
     n, r = a.split(":"); lo, hi = r.split("-"); phases.append((n, int(lo), int(hi)))
+if not phases:  # the numbered phase comments of the current dvs_tile_fast.cuh
+    import re
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(here, "pydvs_b200", "csrc", "dvs_tile_fast.cuh")).read().splitlines()
+    marks = [i + 1 for i, l in enumerate(src) if re.search(r"// ---- [1-4][ab]?\. ", l)]
+    end = next(i + 1 for i, l in enumerate(src) if "write_counters(A, s_idx, t_idx, hist, nh, n_pos_tile, n_neg_tile);" in l)
+    names = ["1 loads", "2 threshold + inhibition + threshold store", "3 scan + work-list push", "4a spike loop", "4b copy-out + counters"]
+    for k, (n, ln) in enumerate(zip(names, marks)):
+        phases.append((n, ln, marks[k + 1] - 1 if k + 1 < len(marks) else end))
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 cur, hdr = None, None
 ins, smp = defaultdict(int), defaultdict(int)
