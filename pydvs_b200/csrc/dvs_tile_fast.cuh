@@ -460,8 +460,8 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
 
   // ---- 4a. one candidate per lane: reference update, list membership, histogram, staged record ------
   // 32-candidate chunks per warp = ceil(ceil(n_cand / 32) / NW), without an integer division by the run-time NW
-  int chunks_per_warp = 1;
-  while (chunks_per_warp * NW < ((n_cand + 31) >> 5)) ++chunks_per_warp;
+  // (inv_nw = ceil(2^16 / NW), set by the launcher: exact for the <= 64 + NW chunks a tile can have)
+  const int chunks_per_warp = (int)(((unsigned)(((n_cand + 31) >> 5) + NW - 1) * A.inv_nw) >> 16);
   const int per_warp = chunks_per_warp << 5;
   const int lo = min(n_cand, warp * per_warp), hi = min(n_cand, lo + per_warp);
   const unsigned magic = A.upd.div_thr.magic;
@@ -659,7 +659,9 @@ __global__ void __launch_bounds__(256, FAST2S_MINB) k_tile_fast2s(const __grid_c
 }
 
 template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT = false>
-static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
+static int launch_fast2(const TileArgs &A_in, int bd, cudaStream_t st) {
+  TileArgs A = A_in;
+  A.inv_nw = (65536u + (unsigned)(bd / 32) - 1u) / (unsigned)(bd / 32);
   auto k = k_tile_fast2<SRC, JH, PAIR, ENC, ADAPT>;
   const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
   const size_t smem = kFastCap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t) + (ADAPT ? kFastCap * 2 : 0) + 256;
@@ -705,7 +707,9 @@ static int launch_fast2(const TileArgs &A, int bd, cudaStream_t st) {
 }
 
 template <int SRC, int ENC, bool ADAPT>
-static int launch_fast4(const TileArgs &A, cudaStream_t st) {
+static int launch_fast4(const TileArgs &A_in, cudaStream_t st) {
+  TileArgs A = A_in;
+  A.inv_nw = (65536u + (unsigned)((A.W / 8 + 31) / 32) - 1u) / (unsigned)((A.W / 8 + 31) / 32);
   const int nh = A.enc.n_slots + 1;
   const size_t smem = kFastCap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t) + (ADAPT ? kFastCap * 2 : 0) + 256;
   cudaError_t e;

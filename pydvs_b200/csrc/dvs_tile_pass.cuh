@@ -19,6 +19,7 @@ struct TileArgs {
   int adaptive, polarity, uncoded, inh_k, vec_ok, fast_hist, drop_silent, use_staged;
   int thr_scalar;
   unsigned inv_w;          // ceil(2^32 / W): q / W == umulhi(q, inv_w) for q < 32768
+  unsigned inv_nw;         // fast kernels: ceil(2^16 / warps per CTA)
   UpdateArgs upd;
   EncArgs enc;
   const void *curr;        // frames (SRC_I16 / SRC_U8) or spikes plane (SRC_PLANES)
