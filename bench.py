@@ -98,6 +98,7 @@ def parse_args():
     ap.add_argument("--pipeline-depth", type=int, default=1, choices=[1, 2])
     ap.add_argument("--k1-variant", default="auto", choices=["auto", "plain", "staged", "generic"],
                     help="generic: force the generic tile body (what shapes outside the fast paths run)")
+    ap.add_argument("--tile-rows", type=int, default=None, help="rows per tile (default: dvs_choose_tile_rows)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="CUDA-graph replay of the step (auto: DVSStreams decides by problem size)")
     ap.add_argument("--settle", type=int, default=24,
@@ -433,7 +434,7 @@ class Case:
         cfg = DVSConfig(width=self.W, height=self.H, streams=S, output_type=wl["output_type"], threshold=12,
                         adaptive_threshold=wl["adaptive"], history_weight=wl["hw"], max_time_ms=wl["max_time_ms"],
                         num_bins=wl["num_bins"], inh_area_width=wl["inh"], frame_dtype=frame_dtype,
-                        threshold0=12 if wl["adaptive"] else None, ref0=wl["ref0"])
+                        threshold0=12 if wl["adaptive"] else None, ref0=wl["ref0"], tile_rows=getattr(args, "tile_rows", None))
         g = {"auto": "auto", "on": True, "off": False}[graph]
         self.dvs = DVSStreams(cfg, device=device, event_capacity=1 << 16, pipeline_depth=pipeline_depth,
                               force_generic={"auto": 0, "plain": 0, "staged": 3, "generic": 1}[k1_variant],
@@ -484,6 +485,8 @@ class Case:
         try:
             dvs.check_status()
         except OverflowError:
+            if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+                raise   # a retry on one rank would leave the others at the barrier
             dvs.reserve_events(2 * dvs.event_capacity)
             return self.timed(K, warmup, barrier, sampler, split)
         split = split and not dvs.use_graph
@@ -518,6 +521,8 @@ class Case:
         try:
             dvs.check_status()
         except OverflowError:   # events were dropped: the step did less work than it should have; measure again
+            if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+                raise
             dvs.reserve_events(2 * dvs.event_capacity)
             return self.timed(K, warmup, barrier, None, split)
         out["events_last_step"] = int(dvs.seg_offsets[-1].item())

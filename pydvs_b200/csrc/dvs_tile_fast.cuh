@@ -38,6 +38,9 @@ DEV uint4 ld16_stream(const void *p) { return __ldcs(reinterpret_cast<const uint
 #ifndef FAST2_PAIR_XY
 #define FAST2_PAIR_XY 1      // two-row tiles: row / column of a candidate by one compare instead of a multiply-high
 #endif
+#ifndef FAST2_J2
+#define FAST2_J2 0           // linear tiles of 257..512 groups with two groups per thread (else four)
+#endif
 #ifndef FAST2_QONLY_ADAPT
 #define FAST2_QONLY_ADAPT 0  // index-only work list for the adaptive kernels as well
 #endif
@@ -766,6 +769,9 @@ static int dispatch_fast_shapes(const TileArgs &A, cudaStream_t st) {
                            : launch_fast2<SRC, JH_, PAIR_, ENC_ANY, ADAPT>(A, BD_, st))
   if (A.inh_k != 2) {
     if (items <= 256) return DVS_LAUNCH_ENC(1, false, round32(items));
+#if FAST2_J2
+    if (items <= 512) return DVS_LAUNCH_ENC(2, false, round32((items + 1) / 2));  // two groups per thread: half the registers
+#endif
     return DVS_LAUNCH_ENC(4, false, round32((items + 3) / 4));
   }
   const int gpr = A.W / 8;  // two-row tiles: each thread owns the same column block(s) in both rows

@@ -5,6 +5,12 @@
 
 #include "dvs_device.cuh"
 
+#ifndef GENERIC_J1
+#define GENERIC_J1 1   // generic body with one group per thread and CTAs of up to 1024 threads: a quarter of the code of the
+                       // four-group form, whose problem is instruction-cache misses (profiles/r2_k1_generic_*): dense 4K
+                       // x 16 streams 1.94 -> 1.53 ms, moving bar 1.27 -> 1.23 ms
+#endif
+
 namespace dvs {
 
 // ================================================================================================
@@ -463,6 +469,9 @@ static int launch_tile_pass(const TileArgs &A, cudaStream_t st) {
   if ((long long)A.S * A.tiles_per_stream > 0x7fffffffll) return set_error(DVS_ERR_UNSUPPORTED, "too many tiles");
   auto round32 = [](int x) { return (x + 31) / 32 * 32; };
   if (items <= 256) return launch_shape<SRC, 1, 256, ADAPT, KI>(A, round32(items), smem, st);
+#if GENERIC_J1
+  if (items <= 1024) return launch_shape<SRC, 1, 1024, ADAPT, KI>(A, round32(items), smem, st);
+#endif
   if (items <= 1024) return launch_shape<SRC, 4, 256, ADAPT, KI>(A, round32((items + 3) / 4), smem, st);
   if constexpr (KI == INH_GENERIC || SRC == SRC_PLANES) {
     const int bd = round32((items + 3) / 4);
