@@ -41,6 +41,9 @@ DEV uint4 ld16_stream(const void *p) { return __ldcs(reinterpret_cast<const uint
 #ifndef FAST2_J2
 #define FAST2_J2 0           // linear tiles of 257..512 groups with two groups per thread (else four)
 #endif
+#ifndef FAST2_FUSED2
+#define FAST2_FUSED2 1       // fused threshold + 2x2 inhibition + entry build (see FUSED2 below)
+#endif
 #ifndef FAST2_QONLY_ADAPT
 #define FAST2_QONLY_ADAPT 0  // index-only work list for the adaptive kernels as well
 #endif
@@ -89,6 +92,15 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
 #define FAST2_QONLY_MODE 2
 #endif
   constexpr bool QONLY = QUAD || (SIMPLE && (FAST2_QONLY_MODE == 1 || (FAST2_QONLY_MODE == 2 && (ADAPT ? FAST2_QONLY_ADAPT != 0 : (!PAIR || SRC == SRC_U8)))));
+  // ADAPT with the index-only list: the thresholds are written back AFTER the spike loop (behind its barrier), so the
+  // lane that takes a candidate reads the old threshold from the plane like the frame and reference pixels, and the
+  // push stores nothing but the index
+  constexpr bool TLATE = ADAPT && QONLY && FAST2_QONLY_ADAPT == 2;
+  // 2x2 tiles, static threshold, inlined encoder, int16 frames (the headline kernel): threshold, inhibition and the
+  // work-list entry of each area's winner are computed in one pass over the area words while frame and reference are at
+  // hand -- the winner's abs_diff, position and sign all come out of one packed key maximum -- so the push after the
+  // scan only stores finished entries
+  constexpr bool FUSED2 = FAST2_FUSED2 && PAIR && !QUAD && !ADAPT && SIMPLE && !QONLY;
   uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
   uint16_t *wl16 = reinterpret_cast<uint16_t *>(smem_raw);  // ENC != 0: pixel indices only
   uint2 *rec_sm = reinterpret_cast<uint2 *>(smem_raw + kFastCap * 4);
@@ -169,6 +181,41 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     const uint32_t f = ADAPT ? ~((t_pk[ADAPT ? j : 0][w] | 0x80008000u) - a) & 0x80008000u : (a + kadd) & 0x80008000u;
     return a & ((f >> 15) * 0xffffu);
   };
+  uint32_t wle[FUSED2 ? JH : 1][4];  // FUSED2: finished work-list entry of each area (0 = none)
+  if constexpr (FUSED2) {
+#pragma unroll
+    for (int h = 0; h < JH; ++h) {
+      const int ju = h, jl = JH + h;
+      flags8[ju] = 0; flags8[jl] = 0;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) wle[h][w] = 0u;
+      if (!have[ju]) continue;
+      rng |= ((r_pk[ju][0] | r_pk[ju][1] | r_pk[ju][2]) | r_pk[ju][3]) | ((r_pk[jl][0] | r_pk[jl][1] | r_pk[jl][2]) | r_pk[jl][3]);
+      rng |= ((c_pk[ju][0] | c_pk[ju][1] | c_pk[ju][2]) | c_pk[ju][3]) | ((c_pk[jl][0] | c_pk[jl][1] | c_pk[jl][2]) | c_pk[jl][3]);
+      const int qu = q0_of(ju);
+      uint32_t ku = 0, kl = 0;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t cu = c_pk[ju][w], ru = r_pk[ju][w], cl = c_pk[jl][w], rl = r_pk[jl][w];
+        const uint32_t au = __vmaxu2(cu, ru) - __vminu2(cu, ru), al = __vmaxu2(cl, rl) - __vminu2(cl, rl);
+        const uint32_t fu = (au + kadd) & 0x80008000u, fl2 = (al + kadd) & 0x80008000u;  // thresholded_difference gs:67-78
+        if ((fu | fl2) == 0u) continue;
+        // local_inhibition gs:177-221 + argmax gs:118-132: keys abs_diff * 8 + (3 - index) * 2 + (frame < reference);
+        // the maximum key is the first maximum of abs_diff * spikes in row-major order and carries its sign
+        const uint32_t mu = au & ((fu >> 15) * 0xffffu), ml = al & ((fl2 >> 15) * 0xffffu);
+        const uint32_t nu = (~((cu | 0x80008000u) - ru) >> 15) & 0x00010001u;  // lane bit: frame < reference
+        const uint32_t nl = (~((cl | 0x80008000u) - rl) >> 15) & 0x00010001u;
+        const uint32_t m2 = __vmaxu2(mu * 8u + 0x00040006u + nu, ml * 8u + 0x00000002u + nl);
+        const uint32_t m = max(m2 & 0xffffu, m2 >> 16);
+        const uint32_t idx = 3u - ((m >> 1) & 3u), half = idx & 1u;
+        const uint32_t r_w = idx < 2u ? ru : rl;
+        const uint32_t q = (uint32_t)qu + (idx < 2u ? 0u : (uint32_t)A.W) + 2u * w + half;
+        wle[h][w] = q | (((r_w >> (16u * half)) & 0xffu) << 13) | ((m >> 3) << 21) | ((m & 1u) << 29);
+        if (idx < 2u) ku |= 1u << (2 * w + half); else kl |= 1u << (2 * w + half);
+      }
+      flags8[ju] = ku; flags8[jl] = kl;
+    }
+  } else {
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     flags8[j] = 0;
@@ -188,6 +235,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
 #pragma unroll
       for (int w = 0; w < 4; ++w) flags8[j] |= (((fl[w] >> 15) & 1u) | ((fl[w] >> 30) & 2u)) << (2 * w);
     }
+  }
   }
   if (ADAPT) {
     // a negative threshold (bit 15 as an unsigned lane), or -- coded rule -- one so large that th + up leaves int16
@@ -223,7 +271,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
 #pragma unroll
       for (int r4 = 0; r4 < 4; ++r4) flags8[r4] = keep[r4];
     }
-  } else if (PAIR) {
+  } else if (PAIR && !FUSED2) {
     // local_inhibition gs:177-221 on registers: of each 2x2 area (word w of the upper and of the lower
     // row group) only the first arg-max of abs_diff * spikes keeps its spike (row-major, strict '>')
 #pragma unroll
@@ -366,7 +414,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     if (tid == 0) A.redo[1 + atomicAdd(A.redo, 1)] = tile;
     return;
   }
-  if (ADAPT) store_thresholds();
+  if (ADAPT && !TLATE) store_thresholds();
   if (decay) store_decayed_reference();
   {
     // entry: tile-local pixel index (13 bits) | reference << 13 (8 bits) | abs_diff << 21 (8 bits) | negative << 29
@@ -381,7 +429,20 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     for (int j = 0; j < J; ++j)
       pos_of[j] = __reduce_add_sync(kFull, (lane < j * NW + warp ? ent : 0u) + (lane + 32 < j * NW + warp ? ent2 : 0u)) +
                   (((j < 2 ? ex_lo : ex_hi) >> (16 * (j & 1))) & 0xffffu);  // + candidates of earlier (group, warp) pairs
-    if (QONLY && PAIR && !QUAD) {
+    if (FUSED2) {
+      // the entries were finished with the inhibition: store them at their ranks (at most one per area)
+#pragma unroll
+      for (int h = 0; h < JH; ++h) {
+        const int ju = h, jl = JH + h;
+        if ((flags8[ju] | flags8[jl]) == 0) continue;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t e = wle[h][w];
+          if (e == 0u) continue;
+          if ((flags8[ju] >> (2 * w)) & 3u) wl[pos_of[ju]++] = e; else wl[pos_of[jl]++] = e;
+        }
+      }
+    } else if (QONLY && PAIR && !QUAD) {
       // index-only entries: one 16-bit store per surviving area
 #pragma unroll
       for (int h = 0; h < JH; ++h) {
@@ -395,7 +456,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
           const bool up = bu != 0;
           const int half = (int)((up ? bu : bl) >> 1);
           const uint32_t pos = up ? pos_of[ju] : pos_of[jl];
-          if (ADAPT) wl_thr[pos] = (uint16_t)((up ? t_pk[ADAPT ? ju : 0][w] : t_pk[ADAPT ? jl : 0][w]) >> (16 * half));
+          if (ADAPT && !TLATE) wl_thr[pos] = (uint16_t)((up ? t_pk[ADAPT ? ju : 0][w] : t_pk[ADAPT ? jl : 0][w]) >> (16 * half));
           wl16[pos] = (uint16_t)((up ? qu : ql) + 2 * w + half);
           if (up) pos_of[ju] = pos + 1; else pos_of[jl] = pos + 1;
         }
@@ -408,7 +469,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
         uint32_t pos = pos_of[j];
         for (uint32_t m = flags8[j]; m; m &= m - 1) {  // candidates only
           const int p = __ffs(m) - 1;
-          if (ADAPT) {
+          if (ADAPT && !TLATE) {
             const unsigned long long t_lo = ((unsigned long long)t_pk[ADAPT ? j : 0][1] << 32) | t_pk[ADAPT ? j : 0][0],
                                      t_hi = ((unsigned long long)t_pk[ADAPT ? j : 0][3] << 32) | t_pk[ADAPT ? j : 0][2];
             wl_thr[pos] = (uint16_t)((p < 4 ? t_lo : t_hi) >> (16 * (p & 3)));
@@ -498,7 +559,10 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       if (FAST2_PAIR_XY && SRC == SRC_I16 && PAIR && !QUAD) { y = q >= A.W ? 1 : 0; x = q - (y ? A.W : 0); }  // two-row tiles
       else { y = (int)__umulhi((unsigned)q, A.inv_w); x = q - y * A.W; }
       int upd;
-      if (ADAPT) upd = SIMPLE ? adpt_div(a, (int)wl_thr[i]) : np_floordiv(a, (int)wl_thr[i]);  // gs:287-289: (a // thr) [* min_threshold below]
+      if (ADAPT) {  // gs:287-289: (a // thr) [* min_threshold below]
+        const int th_old = TLATE ? (int)reinterpret_cast<const uint16_t *>(thr_t)[q] : (int)wl_thr[i];
+        upd = SIMPLE ? adpt_div(a, th_old) : np_floordiv(a, th_old);
+      }
       else if (SIMPLE || A.upd.mode == DVS_UPD_RATE) upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;  // gs:244-249
       else {  // time-binary updates gs:374-376 / gs:421-423: log2 table of abs_diff (raw) or of abs_diff // T
         const int idx = A.upd.mode == DVS_UPD_TIME_BIN_THR ? (int)__umulhi((unsigned)a, magic) : a;
@@ -544,6 +608,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     if (status && lane == 0 && A.status) atomicOr(A.status, (int)status);
   }
   __syncthreads();
+  if (TLATE) store_thresholds();  // every candidate has read its old threshold by now
   uint32_t base = 0, totals = 0;
   {
     const uint32_t t = lane < NW ? wtot[64 + lane] : 0u;  // pos | neg << 16 per warp: the packed sums cannot carry
