@@ -7,15 +7,18 @@ rep = sys.argv[1]
 phases = []
 for a in sys.argv[2:]:
     n, r = a.split(":"); lo, hi = r.split("-"); phases.append((n, int(lo), int(hi)))
-if not phases:  # the numbered phase comments of the current dvs_tile_fast.cuh
-    import re
-    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    src = open(os.path.join(here, "pydvs_b200", "csrc", "dvs_tile_fast.cuh")).read().splitlines()
-    marks = [i + 1 for i, l in enumerate(src) if re.search(r"// ---- [1-4][ab]?\. ", l)]
-    end = next(i + 1 for i, l in enumerate(src) if "write_counters(A, s_idx, t_idx, hist, nh, n_pos_tile, n_neg_tile);" in l)
-    names = ["1 loads", "2 threshold + inhibition + threshold store", "3 scan + work-list push", "4a spike loop", "4b copy-out + counters"]
-    for k, (n, ln) in enumerate(zip(names, marks)):
-        phases.append((n, ln, marks[k + 1] - 1 if k + 1 < len(marks) else end))
+import re
+here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+file_phases = {}  # file name -> [(name, lo, hi)]
+if phases:
+    file_phases["dvs_tile_fast.cuh"] = phases
+else:  # the numbered phase comments ("// ---- 2. ...") of the kernel headers
+    for fn in ("dvs_tile_fast.cuh", "dvs_tile_ranked.cuh"):
+        try: src = open(os.path.join(here, "pydvs_b200", "csrc", fn)).read().splitlines()
+        except OSError: continue
+        marks = [(i + 1, re.search(r"// ---- ([1-4][ab]?\. [^-]*)", l).group(1).strip()) for i, l in enumerate(src) if re.search(r"// ---- [1-4][ab]?\. ", l)]
+        end = max(i + 1 for i, l in enumerate(src) if "write_counters(A, s_idx, t_idx, hist, nh" in l)
+        file_phases[fn] = [(n[:44], ln, marks[k + 1][0] - 1 if k + 1 < len(marks) else end) for k, (ln, n) in enumerate(marks)]
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 cur, hdr = None, None
 ins, smp = defaultdict(int), defaultdict(int)
@@ -28,11 +31,11 @@ for r in csv.reader(io.StringIO(txt)):
         try: i, s = int(d["Instructions Executed"]), int(d["# Samples"])
         except Exception: continue
         key = cur
-        if cur == "dvs_tile_fast.cuh":
-            key = "fast:other"
-            for n, lo, hi in phases:
+        if cur in file_phases:
+            key = cur + ":other"
+            for n, lo, hi in file_phases[cur]:
                 if lo <= int(r[0]) <= hi: key = n; break
         ins[key] += i; smp[key] += s
 ti, ts = sum(ins.values()) or 1, sum(smp.values()) or 1
 for k in sorted(ins, key=lambda k: -ins[k]):
-    print("%-28s %6.1f%% inst (%d)  %5.1f%% samples" % (k, 100.0 * ins[k] / ti, ins[k], 100.0 * smp[k] / ts))
+    print("%-46s %6.1f%% inst (%d)  %5.1f%% samples" % (k, 100.0 * ins[k] / ti, ins[k], 100.0 * smp[k] / ts))

@@ -812,6 +812,13 @@ static int launch_fast4(const TileArgs &A_in, cudaStream_t st) {
   return DVS_OK;
 }
 
+// the ranked form of the headline shape (dvs_tile_ranked.cuh; the translation units include that header)
+#ifndef FAST2_RANKED
+#define FAST2_RANKED 1
+#endif
+template <int SRC, int JH, int ENC>
+static int launch_ranked(const TileArgs &A_in, int bd, cudaStream_t st);
+
 // Caller guarantees: vec_ok (incl. the threshold plane when ADAPT), W % 8 == 0, <= 1024 groups per tile, inhibition
 // off or 2x2 on two-row tiles; static: 2 <= T, rate or time-binary update, history_weight in [0, 1], max_time_ms >= 0;
 // adaptive: rate_adpt update, history_weight in [0, 1], 0 <= min <= max <= 32767, 0 <= up, down <= 32767; no debug planes.
@@ -844,6 +851,15 @@ static int dispatch_fast_shapes(const TileArgs &A, cudaStream_t st) {
     return DVS_LAUNCH_ENC(4, false, round32((items + 3) / 4));
   }
   const int gpr = A.W / 8;  // two-row tiles: each thread owns the same column block(s) in both rows
+  if constexpr (FAST2_RANKED && !ADAPT) {
+    if (enc != ENC_ANY && A.use_staged == 0) {
+      if (gpr <= 256)
+        return enc == ENC_RATE_CODED ? launch_ranked<SRC, 1, ENC_RATE_CODED>(A, round32(gpr), st)
+                                     : launch_ranked<SRC, 1, ENC_TIME_CODED>(A, round32(gpr), st);
+      return enc == ENC_RATE_CODED ? launch_ranked<SRC, 2, ENC_RATE_CODED>(A, round32((gpr + 1) / 2), st)
+                                   : launch_ranked<SRC, 2, ENC_TIME_CODED>(A, round32((gpr + 1) / 2), st);
+    }
+  }
   if (gpr <= 256) return DVS_LAUNCH_ENC(1, true, round32(gpr));
   return DVS_LAUNCH_ENC(2, true, round32((gpr + 1) / 2));
 #undef DVS_LAUNCH_ENC

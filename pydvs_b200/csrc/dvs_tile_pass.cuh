@@ -26,6 +26,7 @@ struct TileArgs {
   int thr_scalar;
   unsigned inv_w;          // ceil(2^32 / W): q / W == umulhi(q, inv_w) for q < 32768
   unsigned inv_nw;         // fast kernels: ceil(2^16 / warps per CTA)
+  int silent_a;            // ranked kernel: abs_diff from which a coded-rate spike falls in no slot (and is not recorded)
   UpdateArgs upd;
   EncArgs enc;
   const void *curr;        // frames (SRC_I16 / SRC_U8) or spikes plane (SRC_PLANES)

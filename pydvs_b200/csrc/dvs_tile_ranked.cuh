@@ -1,0 +1,253 @@
+// dvs_tile_ranked.cuh -- K1 for the headline shape: static threshold, 2x2 inhibition on two-row tiles, coded RATE or
+// TIME encoder with MERGED lists, history_weight == 1, int16 or uint8 frames (what dispatch_fast_shapes calls the
+// FUSED2 shape).  Same contract and bit-exact results as fast2_tile / the generic tile pass; the difference is that
+// every candidate knows its FINAL rank in the tile's pos / neg list before the per-candidate phase starts:
+//
+//   2. one pass over the 2x2 areas a thread owns (frame + reference words of both rows at hand): threshold, first
+//      arg-max through a packed key maximum, and the finished work-list entry of the winner (pixel index, reference,
+//      abs_diff, sign, "silent" = a coded-rate spike that falls in no slot and is not recorded);  the thread counts its
+//      pos and neg winners per row in 8-bit fields;
+//   3. ONE warp scan of those packed counts (a warp holds at most 128 per field) + the per-(row, warp) totals through
+//      shared memory give each winner its rank among the tile's pos resp. neg spikes in row-major order, and the tile
+//      totals -- the work list is laid out [pos in list order][neg in list order][silent, any order];
+//   4. one candidate per lane: reference update, slot histogram, and the record goes STRAIGHT to its place in the tile's
+//      list in global memory (lane i of the pos part writes record i: consecutive lanes, consecutive 8-byte records).
+//      No ballots, no ranks, no staging in shared memory, no copy-out pass and one barrier less than fast2_tile, which
+//      discovers list membership only inside the per-candidate loop.
+//
+// Shared memory: [wl: kFastCap u32][wtot: 32 u32][hist: 2 * (n_slots + 1) u32][misc: 4 u32]  (~8.5 KB)
+#pragma once
+#include "dvs_tile_fast.cuh"
+
+namespace dvs {
+
+#ifndef FAST2R_MINB
+#define FAST2R_MINB 5
+#endif
+
+template <int SRC, int JH, int ENC>
+DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigned char *smem_raw) {
+  static_assert(ENC == ENC_RATE_CODED || ENC == ENC_TIME_CODED, "inlined encoders only");
+  constexpr int J = 2 * JH;
+  uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
+  uint32_t *wtot = wl + kFastCap;
+  uint32_t *hist = wtot + 32;
+  const int nh = A.enc.n_slots + 1;
+  uint32_t *misc = hist + 2 * nh;  // [0]: silent candidates claimed so far
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;  // J * NW <= 32
+  const int tile = s_idx * A.tiles_per_stream + t_idx;
+  const int row0 = t_idx * 2;
+  const size_t plane_off = ((size_t)s_idx * A.H + row0) * A.W;
+  int16_t *const ref_t = A.ref + plane_off;
+  const int gpr = A.W >> 3;  // groups of 8 pixels per row
+  const unsigned char *const cur_thread =
+      static_cast<const unsigned char *>(A.curr) + (plane_off + (size_t)tid * 8) * (SRC == SRC_U8 ? 1 : 2);
+  const int16_t *const ref_thread = ref_t + tid * 8;
+
+  // ---- 1. loads: group j = row (j / JH), column block (j % JH); all requests in flight before first use -------------
+  uint32_t c_pk[J][4], r_pk[J][4];
+  bool have[JH];
+#pragma unroll
+  for (int h = 0; h < JH; ++h) have[h] = h * (int)blockDim.x + tid < gpr;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int off = (j / JH) * A.W + (j % JH) * (int)blockDim.x * 8;
+    if (have[j % JH]) {
+      if (SRC == SRC_U8) {
+        const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(cur_thread + off));
+        c_pk[j][0] = __byte_perm(v.x, 0, 0x4140); c_pk[j][1] = __byte_perm(v.x, 0, 0x4342);
+        c_pk[j][2] = __byte_perm(v.y, 0, 0x4140); c_pk[j][3] = __byte_perm(v.y, 0, 0x4342);
+      } else {
+        const uint4 v = ld16_stream(cur_thread + 2 * off);
+        c_pk[j][0] = v.x; c_pk[j][1] = v.y; c_pk[j][2] = v.z; c_pk[j][3] = v.w;
+      }
+      const uint4 r = ld16(ref_thread + off);
+      r_pk[j][0] = r.x; r_pk[j][1] = r.y; r_pk[j][2] = r.z; r_pk[j][3] = r.w;
+    }
+  }
+  if (tid < 2 * nh) hist[tid] = 0;
+  for (int i = blockDim.x + tid; i < 2 * nh; i += blockDim.x) hist[i] = 0;
+  if (tid == 0) misc[0] = 0;
+
+  // ---- 2. threshold + 2x2 inhibition + finished entries + class counts ----------------------------------------------
+  const int T = A.thr_scalar;                                  // 2 <= T <= 32767 (host-checked)
+  const uint32_t kadd = (uint32_t)(0x7fff - T) * 0x00010001u;  // bit 15 of (a + kadd) <=> a > T
+  // entry: tile-local pixel index (13 bits) | reference << 13 (8) | abs_diff << 21 (8) | negative << 29 | silent << 30
+  uint32_t wle[JH][4];
+  uint32_t rowbits = 0;        // bit (4 * h + w): the winner of that area sits in the lower row
+  uint32_t cp = 0, cn = 0;     // pos / neg winners of this thread per group j, 8-bit fields
+  uint32_t rng = 0;
+  bool silent_any = false;
+#pragma unroll
+  for (int h = 0; h < JH; ++h) {
+    const int ju = h, jl = JH + h;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) wle[h][w] = 0u;
+    if (!have[h]) continue;
+    rng |= ((r_pk[ju][0] | r_pk[ju][1] | r_pk[ju][2]) | r_pk[ju][3]) | ((r_pk[jl][0] | r_pk[jl][1] | r_pk[jl][2]) | r_pk[jl][3]);
+    if (SRC != SRC_U8)
+      rng |= ((c_pk[ju][0] | c_pk[ju][1] | c_pk[ju][2]) | c_pk[ju][3]) | ((c_pk[jl][0] | c_pk[jl][1] | c_pk[jl][2]) | c_pk[jl][3]);
+    const uint32_t qu = (uint32_t)(h * (int)blockDim.x * 8 + tid * 8);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint32_t cu = c_pk[ju][w], ru = r_pk[ju][w], cl = c_pk[jl][w], rl = r_pk[jl][w];
+      const uint32_t au = __vmaxu2(cu, ru) - __vminu2(cu, ru), al = __vmaxu2(cl, rl) - __vminu2(cl, rl);
+      const uint32_t fu = (au + kadd) & 0x80008000u, fl2 = (al + kadd) & 0x80008000u;  // thresholded_difference gs:67-78
+      if ((fu | fl2) == 0u) continue;
+      // local_inhibition gs:177-221 + argmax gs:118-132: keys abs_diff * 8 + (3 - index) * 2 + (frame < reference); the
+      // maximum key is the first maximum of abs_diff * spikes in row-major order and carries its sign
+      const uint32_t mu = au & ((fu >> 15) * 0xffffu), ml = al & ((fl2 >> 15) * 0xffffu);
+      const uint32_t nu = (~((cu | 0x80008000u) - ru) >> 15) & 0x00010001u;  // lane bit: frame < reference
+      const uint32_t nl = (~((cl | 0x80008000u) - rl) >> 15) & 0x00010001u;
+      const uint32_t m2 = __vmaxu2(mu * 8u + 0x00040006u + nu, ml * 8u + 0x00000002u + nl);
+      const uint32_t m = max(m2 & 0xffffu, m2 >> 16);
+      const uint32_t idx = 3u - ((m >> 1) & 3u), half = idx & 1u, lower = idx >> 1;
+      const uint32_t r_w = lower ? rl : ru;
+      const uint32_t a_win = m >> 3, neg = m & 1u;
+      const uint32_t silent = a_win >= (uint32_t)A.silent_a ? 1u : 0u;  // coded rate, k == 0, records not wanted
+      const uint32_t q = qu + (lower ? (uint32_t)A.W : 0u) + 2u * w + half;
+      wle[h][w] = q | (((r_w >> (16u * half)) & 0xffu) << 13) | (a_win << 21) | (neg << 29) | (silent << 30);
+      rowbits |= lower << (4 * h + w);
+      const uint32_t inc = (silent ? 0u : 1u) << (8 * (lower * JH + h));
+      cp += neg ? 0u : inc;
+      cn += neg ? inc : 0u;
+      silent_any |= silent != 0u;
+    }
+  }
+
+  // ---- 3. ranks: one warp scan of the packed counts, (row, warp) totals through shared memory ------------------------
+  const bool w_unsafe = __any_sync(kFull, (rng & 0xFF00FF00u) != 0);
+  const bool w_silent = __any_sync(kFull, silent_any);
+  uint32_t ip = cp, in = cn;
+  if (__any_sync(kFull, (cp | cn) != 0u)) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y0 = __shfl_up_sync(kFull, ip, o), y1 = __shfl_up_sync(kFull, in, o);
+      if (lane >= o) { ip += y0; in += y1; }
+    }
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+      wtot[j * NW + warp] = ((ip >> (8 * j)) & 0xffu) | (((in >> (8 * j)) & 0xffu) << 16) |
+                            (j == 0 ? (w_unsafe ? 0x80000000u : 0u) | (w_silent ? 0x40000000u : 0u) : 0u);
+  }
+  __syncthreads();
+  const uint32_t ent_raw = lane < J * NW ? wtot[lane] : 0u;  // every warp reads the <= 32 totals
+  const bool unsafe = __any_sync(kFull, (ent_raw >> 31) != 0u);
+  const bool has_silent = __any_sync(kFull, ((ent_raw >> 30) & 1u) != 0u);
+  const uint32_t ent = ent_raw & 0x3fffffffu;
+  const uint32_t totals = __reduce_add_sync(kFull, ent);  // #pos | #neg << 16 of the tile (each <= 2048: no carry)
+  const int n_pos = totals & 0xffffu, n_neg = totals >> 16;
+  if (totals == 0u && !has_silent && !unsafe) {  // quiet tile: no records, no events, reference untouched
+    for (int c = tid; c < A.C; c += blockDim.x)
+      A.tile_counts[((size_t)s_idx * A.C + c) * A.tiles_per_stream + t_idx] = 0;
+    return;
+  }
+  if (unsafe) {  // a pixel outside [0, 255]: the generic body replays the tile with exact int16 wrap semantics
+    if (tid == 0) A.redo[1 + atomicAdd(A.redo, 1)] = tile;
+    return;
+  }
+  {
+    const uint32_t ex_p = ip - cp, ex_n = in - cn;  // exclusive over the lanes of this warp, per group
+    uint32_t bp[J], bn[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const uint32_t b = __reduce_add_sync(kFull, lane < j * NW + warp ? ent : 0u);  // earlier (group, warp) pairs
+      bp[j] = (b & 0xffffu) + ((ex_p >> (8 * j)) & 0xffu);
+      bn[j] = (uint32_t)n_pos + (b >> 16) + ((ex_n >> (8 * j)) & 0xffu);
+    }
+#pragma unroll
+    for (int h = 0; h < JH; ++h) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t e = wle[h][w];
+        if (e == 0u) continue;
+        const bool lower = (rowbits >> (4 * h + w)) & 1u;
+        uint32_t pos;
+        if (e & 0x40000000u) pos = (uint32_t)(n_pos + n_neg) + atomicAdd(&misc[0], 1u);  // silent: order irrelevant
+        else if (e & 0x20000000u) { if (lower) pos = bn[JH + h]++; else pos = bn[h]++; }
+        else { if (lower) pos = bp[JH + h]++; else pos = bp[h]++; }
+        wl[pos] = e;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 4. one candidate per lane: reference update, slot histogram, record straight to its place ---------------------
+  const int n_rec = n_pos + n_neg, n_all = n_rec + (int)misc[0];
+  const int chunks_per_warp = (int)(((unsigned)(((n_all + 31) >> 5) + NW - 1) * A.inv_nw) >> 16);
+  const int per_warp = chunks_per_warp << 5;
+  const int lo = min(n_all, warp * per_warp), hi = min(n_all, lo + per_warp);
+  const unsigned magic = A.upd.div_thr.magic;
+  const int max_n = A.upd.max_time_ms;
+  const size_t region = (size_t)tile * A.rec_stride;
+  dvs_record *const pos_dst = A.records + region;
+  dvs_record *const neg_dst = A.records + region + (A.rec_stride - n_neg) - n_pos;  // indexed by the work-list position
+  unsigned status = 0;
+  for (int i = lo + lane; i < hi; i += 32) {
+    const uint32_t e = wl[i];
+    const int q = e & 0x1fff, r = (e >> 13) & 0xff, a = (e >> 21) & 0xff;
+    const bool neg = (e >> 29) & 1u;
+    const int y = q >= A.W ? 1 : 0, x = q - (y ? A.W : 0);
+    const int upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;  // gs:244-249
+    ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
+    if (i < n_rec) {
+      int desc;
+      if (ENC == ENC_RATE_CODED) {
+        desc = max(0, (A.enc.n_slots - 1) - (int)__umulhi((unsigned)a, A.enc.dv.magic));  // k, gs:830-832
+        atomicAdd(&hist[(neg ? nh : 0) + desc], 1u);
+      } else {
+        // make_spike_lists_time gs:903-926 (see fast2_tile)
+        const int v = (int)__umulhi((unsigned)a, A.enc.dv.magic);
+        int nt = min(v - 1, A.enc.n_slots - 1);
+        if (neg) nt = max(nt, 0);
+        desc = A.enc.n_slots - nt - 1;
+        if (desc >= A.enc.n_slots) { status |= DVS_STATUS_SLOT_RANGE; desc = -1; }
+        else atomicAdd(&hist[(neg ? nh : 0) + desc], 1u);
+      }
+      const uint2 rec = make_uint2((uint32_t)(row0 + y) | ((uint32_t)x << 16), rec_word1(a, desc, true));
+      *reinterpret_cast<uint2 *>((i < n_pos ? pos_dst : neg_dst) + i) = rec;
+    }
+  }
+  if (ENC == ENC_TIME_CODED) {
+    status = __reduce_or_sync(kFull, status);
+    if (status && lane == 0 && A.status) atomicOr(A.status, (int)status);
+  }
+  __syncthreads();
+  write_counters(A, s_idx, t_idx, hist, nh, n_pos, n_neg);
+}
+
+template <int SRC, int JH, int ENC>
+__global__ void __launch_bounds__(256, FAST2R_MINB) k_tile_ranked(const __grid_constant__ TileArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  fast2r_tile<SRC, JH, ENC>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw);
+}
+
+// Caller guarantees the FUSED2 shape (see dispatch_fast_shapes) and two-row tiles of at most 8192 pixels.
+template <int SRC, int JH, int ENC>
+static int launch_ranked(const TileArgs &A_in, int bd, cudaStream_t st) {
+  TileArgs A = A_in;
+  A.inv_nw = (65536u + (unsigned)(bd / 32) - 1u) / (unsigned)(bd / 32);
+  // coded rate with drop_silent: spikes with k == 0 (abs_diff // T_enc >= n_slots - 1) are updated but not recorded
+  A.silent_a = (ENC == ENC_RATE_CODED && A.drop_silent) ? (A.enc.n_slots - 1) * A.enc.threshold : 0x7fffffff;
+  const int nh = A.enc.n_slots + 1;
+  const size_t smem = kFastCap * 4 + (32 + 2 * nh + 4) * sizeof(uint32_t);
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(A.redo, 0, sizeof(int32_t), st)) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+  k_tile_ranked<SRC, JH, ENC><<<dim3((unsigned)A.tiles_per_stream, (unsigned)A.S), bd, smem, st>>>(A);
+  if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+  // generic body over the (normally zero) declined tiles
+  auto kr = k_tile_redo<SRC, 4, INH_K2, false>;
+  const size_t smem_r = ((A.tile_px * 2 + 15) & ~15) + (128 + 2 * nh + 8) * sizeof(uint32_t);
+  if (smem_r > 48 * 1024 && (e = cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)) != cudaSuccess)
+    return set_error((int)e, cudaGetErrorString(e));
+  const int items = A.tile_px / 8;
+  const long long tiles = (long long)A.S * A.tiles_per_stream;
+  kr<<<(unsigned)(tiles < 592 ? tiles : 592), ((items + 3) / 4 + 31) / 32 * 32, smem_r, st>>>(A);
+  if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+  return DVS_OK;
+}
+
+}  // namespace dvs

@@ -1,5 +1,5 @@
 // K1 fast-path instantiations with an adaptive threshold plane, frame dtype SRC_U8 (see dvs_tile_fast.cuh)
-#include "dvs_tile_fast.cuh"
+#include "dvs_tile_ranked.cuh"
 namespace dvs {
 int launch_tile_fast_u8_adpt(const TileArgs &A, cudaStream_t st) { return dispatch_fast_adpt<SRC_U8>(A, st); }
 }  // namespace dvs
