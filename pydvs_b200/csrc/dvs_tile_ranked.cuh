@@ -6,16 +6,17 @@
 //   2. one pass over the 2x2 areas a thread owns (frame + reference words of both rows at hand): threshold, first
 //      arg-max through a packed key maximum, and the finished work-list entry of the winner (pixel index, reference,
 //      abs_diff, sign, "silent" = a coded-rate spike that falls in no slot and is not recorded);  the thread counts its
-//      pos and neg winners per row in 8-bit fields;
+//      recorded pos and neg winners per row in 8-bit fields;
 //   3. ONE warp scan of those packed counts (a warp holds at most 128 per field) + the per-(row, warp) totals through
 //      shared memory give each winner its rank among the tile's pos resp. neg spikes in row-major order, and the tile
-//      totals -- the work list is laid out [pos in list order][neg in list order][silent, any order];
+//      totals -- the work list is laid out [pos in list order][neg in list order]; a silent winner never reaches the
+//      list: its only effect, the reference update, is applied by the owner thread while it stores its entries;
 //   4. one candidate per lane: reference update, slot histogram, and the record goes STRAIGHT to its place in the tile's
 //      list in global memory (lane i of the pos part writes record i: consecutive lanes, consecutive 8-byte records).
 //      No ballots, no ranks, no staging in shared memory, no copy-out pass and one barrier less than fast2_tile, which
 //      discovers list membership only inside the per-candidate loop.
 //
-// Shared memory: [wl: kFastCap u32][wtot: 32 u32][hist: 2 * (n_slots + 1) u32][misc: 4 u32]  (~8.5 KB)
+// Shared memory: [wl: kFastCap u32][wtot: 32 u32][hist: 2 * (n_slots + 1) u32]  (~8.5 KB)
 #pragma once
 #include "dvs_tile_fast.cuh"
 
@@ -25,6 +26,14 @@ namespace dvs {
 #define FAST2R_MINB 5
 #endif
 
+// bit 15 / 31 of x replicated over its 16-bit lane: one PRMT with sign-replicating selectors (byte 1 -> bytes 0, 1;
+// byte 3 -> bytes 2, 3).  __byte_perm() ignores bit 3 of a selector nibble, hence the inline PTX.
+DEV uint32_t msb_lane_mask(uint32_t x) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(0xBB99u));
+  return r;
+}
+
 template <int SRC, int JH, int ENC>
 DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigned char *smem_raw) {
   static_assert(ENC == ENC_RATE_CODED || ENC == ENC_TIME_CODED, "inlined encoders only");
@@ -33,7 +42,6 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
   uint32_t *wtot = wl + kFastCap;
   uint32_t *hist = wtot + 32;
   const int nh = A.enc.n_slots + 1;
-  uint32_t *misc = hist + 2 * nh;  // [0]: silent candidates claimed so far
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;  // J * NW <= 32
   const int tile = s_idx * A.tiles_per_stream + t_idx;
@@ -68,20 +76,19 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
   }
   if (tid < 2 * nh) hist[tid] = 0;
   for (int i = blockDim.x + tid; i < 2 * nh; i += blockDim.x) hist[i] = 0;
-  if (tid == 0) misc[0] = 0;
 
   // ---- 2. threshold + 2x2 inhibition + finished entries + class counts ----------------------------------------------
   const int T = A.thr_scalar;                                  // 2 <= T <= 32767 (host-checked)
   const uint32_t kadd = (uint32_t)(0x7fff - T) * 0x00010001u;  // bit 15 of (a + kadd) <=> a > T
   // entry: tile-local pixel index (13 bits) | reference << 13 (8) | abs_diff << 21 (8) | negative << 29 | silent << 30
   uint32_t wle[JH][4];
-  uint32_t rowbits = 0;        // bit (4 * h + w): the winner of that area sits in the lower row
-  uint32_t cp = 0, cn = 0;     // pos / neg winners of this thread per group j, 8-bit fields
+  uint32_t cnt[JH];  // recorded winners of this thread per column block, 8-bit fields: upper row pos, lower row pos, upper neg, lower neg
+  uint32_t sil = 0;  // bit h: a silent winner in column block h
   uint32_t rng = 0;
-  bool silent_any = false;
 #pragma unroll
   for (int h = 0; h < JH; ++h) {
     const int ju = h, jl = JH + h;
+    cnt[h] = 0;
 #pragma unroll
     for (int w = 0; w < 4; ++w) wle[h][w] = 0u;
     if (!have[h]) continue;
@@ -96,8 +103,9 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
       const uint32_t fu = (au + kadd) & 0x80008000u, fl2 = (al + kadd) & 0x80008000u;  // thresholded_difference gs:67-78
       if ((fu | fl2) == 0u) continue;
       // local_inhibition gs:177-221 + argmax gs:118-132: keys abs_diff * 8 + (3 - index) * 2 + (frame < reference); the
-      // maximum key is the first maximum of abs_diff * spikes in row-major order and carries its sign
-      const uint32_t mu = au & ((fu >> 15) * 0xffffu), ml = al & ((fl2 >> 15) * 0xffffu);
+      // maximum key is the first maximum of abs_diff * spikes in row-major order and carries its sign.  (PRMT with the
+      // sign-replicating selector turns bit 15 / 31 of a flag word into a lane mask in one instruction.)
+      const uint32_t mu = au & msb_lane_mask(fu), ml = al & msb_lane_mask(fl2);
       const uint32_t nu = (~((cu | 0x80008000u) - ru) >> 15) & 0x00010001u;  // lane bit: frame < reference
       const uint32_t nl = (~((cl | 0x80008000u) - rl) >> 15) & 0x00010001u;
       const uint32_t m2 = __vmaxu2(mu * 8u + 0x00040006u + nu, ml * 8u + 0x00000002u + nl);
@@ -105,33 +113,42 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
       const uint32_t idx = 3u - ((m >> 1) & 3u), half = idx & 1u, lower = idx >> 1;
       const uint32_t r_w = lower ? rl : ru;
       const uint32_t a_win = m >> 3, neg = m & 1u;
-      const uint32_t silent = a_win >= (uint32_t)A.silent_a ? 1u : 0u;  // coded rate, k == 0, records not wanted
+      const bool silent = a_win >= (uint32_t)A.silent_a;  // coded rate, k == 0, records not wanted: no event, no record
       const uint32_t q = qu + (lower ? (uint32_t)A.W : 0u) + 2u * w + half;
-      wle[h][w] = q | (((r_w >> (16u * half)) & 0xffu) << 13) | (a_win << 21) | (neg << 29) | (silent << 30);
-      rowbits |= lower << (4 * h + w);
-      const uint32_t inc = (silent ? 0u : 1u) << (8 * (lower * JH + h));
-      cp += neg ? 0u : inc;
-      cn += neg ? inc : 0u;
-      silent_any |= silent != 0u;
+      wle[h][w] = q | (((r_w >> (16u * half)) & 0xffu) << 13) | (a_win << 21) | (neg << 29) | (silent ? 1u << 30 : 0u);
+      if (silent) sil |= 1u << h;
+      else cnt[h] += 1u << (8u * lower + 16u * neg);
     }
   }
 
   // ---- 3. ranks: one warp scan of the packed counts, (row, warp) totals through shared memory ------------------------
   const bool w_unsafe = __any_sync(kFull, (rng & 0xFF00FF00u) != 0);
-  const bool w_silent = __any_sync(kFull, silent_any);
-  uint32_t ip = cp, in = cn;
-  if (__any_sync(kFull, (cp | cn) != 0u)) {
+  const bool w_silent = __any_sync(kFull, sil != 0u);
+  uint32_t inc[JH];
+#pragma unroll
+  for (int h = 0; h < JH; ++h) inc[h] = cnt[h];
+  if (__any_sync(kFull, (cnt[0] | cnt[JH - 1]) != 0u)) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y0 = __shfl_up_sync(kFull, ip, o), y1 = __shfl_up_sync(kFull, in, o);
-      if (lane >= o) { ip += y0; in += y1; }
-    }
-  }
-  if (lane == 31) {
 #pragma unroll
-    for (int j = 0; j < J; ++j)
-      wtot[j * NW + warp] = ((ip >> (8 * j)) & 0xffu) | (((in >> (8 * j)) & 0xffu) << 16) |
-                            (j == 0 ? (w_unsafe ? 0x80000000u : 0u) | (w_silent ? 0x40000000u : 0u) : 0u);
+      for (int h = 0; h < JH; ++h) {
+        const uint32_t y = __shfl_up_sync(kFull, inc[h], o);
+        if (lane >= o) inc[h] += y;
+      }
+    }
+    // group j = row * JH + h; lane j publishes the warp's (pos | neg << 16) total of that group
+    uint32_t tot = __shfl_sync(kFull, inc[0], 31);
+    if (JH == 2) {
+      const uint32_t t1 = __shfl_sync(kFull, inc[JH - 1], 31);
+      if (lane & 1) tot = t1;
+    }
+    if (lane < J) {
+      const int row = JH == 2 ? lane >> 1 : lane;
+      wtot[lane * NW + warp] = ((tot >> (8 * row)) & 0xffu) | (((tot >> (16 + 8 * row)) & 0xffu) << 16) |
+                               (lane == 0 ? (w_unsafe ? 0x80000000u : 0u) | (w_silent ? 0x40000000u : 0u) : 0u);
+    }
+  } else if (lane < J) {
+    wtot[lane * NW + warp] = lane == 0 ? (w_unsafe ? 0x80000000u : 0u) | (w_silent ? 0x40000000u : 0u) : 0u;
   }
   __syncthreads();
   const uint32_t ent_raw = lane < J * NW ? wtot[lane] : 0u;  // every warp reads the <= 32 totals
@@ -149,39 +166,55 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
     if (tid == 0) A.redo[1 + atomicAdd(A.redo, 1)] = tile;
     return;
   }
+  const unsigned magic = A.upd.div_thr.magic;
+  const int max_n = A.upd.max_time_ms;
   {
-    const uint32_t ex_p = ip - cp, ex_n = in - cn;  // exclusive over the lanes of this warp, per group
-    uint32_t bp[J], bn[J];
+    // pn[j]: next pos rank | next neg work-list position << 16 of this thread in group j
+    uint32_t pn[J];
 #pragma unroll
     for (int j = 0; j < J; ++j) {
+      const int h = j % JH, row = j / JH;
       const uint32_t b = __reduce_add_sync(kFull, lane < j * NW + warp ? ent : 0u);  // earlier (group, warp) pairs
-      bp[j] = (b & 0xffffu) + ((ex_p >> (8 * j)) & 0xffu);
-      bn[j] = (uint32_t)n_pos + (b >> 16) + ((ex_n >> (8 * j)) & 0xffu);
+      const uint32_t ex = inc[h] - cnt[h];                                            // earlier lanes of this warp
+      pn[j] = ((b & 0xffffu) + ((ex >> (8 * row)) & 0xffu)) |
+              (((uint32_t)n_pos + (b >> 16) + ((ex >> (16 + 8 * row)) & 0xffu)) << 16);
     }
 #pragma unroll
     for (int h = 0; h < JH; ++h) {
+      if ((cnt[h] | ((sil >> h) & 1u)) == 0u) continue;
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         const uint32_t e = wle[h][w];
         if (e == 0u) continue;
-        const bool lower = (rowbits >> (4 * h + w)) & 1u;
-        uint32_t pos;
-        if (e & 0x40000000u) pos = (uint32_t)(n_pos + n_neg) + atomicAdd(&misc[0], 1u);  // silent: order irrelevant
-        else if (e & 0x20000000u) { if (lower) pos = bn[JH + h]++; else pos = bn[h]++; }
-        else { if (lower) pos = bp[JH + h]++; else pos = bp[h]++; }
-        wl[pos] = e;
+        const int q = e & 0x1fff;
+        const bool neg = (e & 0x20000000u) != 0u;
+        if (e & 0x40000000u) {
+          // silent spike: its only effect is the reference update (gs:244-249), done right here by the owner thread
+          const int r = (e >> 13) & 0xff, a = (e >> 21) & 0xff;
+          const int upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;
+          ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
+        } else {
+          const bool lower = q >= A.W;
+          const uint32_t x = lower ? pn[JH + h] : pn[h];
+          wl[neg ? x >> 16 : x & 0xffffu] = e;
+          const uint32_t nx = x + (neg ? 0x10000u : 1u);
+          if (lower) pn[JH + h] = nx; else pn[h] = nx;
+        }
       }
     }
+  }
+  const int n_rec = n_pos + n_neg;
+  if (n_rec == 0) {  // silent spikes only: references are updated, nothing to list
+    for (int c = tid; c < A.C; c += blockDim.x)
+      A.tile_counts[((size_t)s_idx * A.C + c) * A.tiles_per_stream + t_idx] = 0;
+    return;
   }
   __syncthreads();
 
   // ---- 4. one candidate per lane: reference update, slot histogram, record straight to its place ---------------------
-  const int n_rec = n_pos + n_neg, n_all = n_rec + (int)misc[0];
-  const int chunks_per_warp = (int)(((unsigned)(((n_all + 31) >> 5) + NW - 1) * A.inv_nw) >> 16);
+  const int chunks_per_warp = (int)(((unsigned)(((n_rec + 31) >> 5) + NW - 1) * A.inv_nw) >> 16);
   const int per_warp = chunks_per_warp << 5;
-  const int lo = min(n_all, warp * per_warp), hi = min(n_all, lo + per_warp);
-  const unsigned magic = A.upd.div_thr.magic;
-  const int max_n = A.upd.max_time_ms;
+  const int lo = min(n_rec, warp * per_warp), hi = min(n_rec, lo + per_warp);
   const size_t region = (size_t)tile * A.rec_stride;
   dvs_record *const pos_dst = A.records + region;
   dvs_record *const neg_dst = A.records + region + (A.rec_stride - n_neg) - n_pos;  // indexed by the work-list position
@@ -193,23 +226,21 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
     const int y = q >= A.W ? 1 : 0, x = q - (y ? A.W : 0);
     const int upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;  // gs:244-249
     ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
-    if (i < n_rec) {
-      int desc;
-      if (ENC == ENC_RATE_CODED) {
-        desc = max(0, (A.enc.n_slots - 1) - (int)__umulhi((unsigned)a, A.enc.dv.magic));  // k, gs:830-832
-        atomicAdd(&hist[(neg ? nh : 0) + desc], 1u);
-      } else {
-        // make_spike_lists_time gs:903-926 (see fast2_tile)
-        const int v = (int)__umulhi((unsigned)a, A.enc.dv.magic);
-        int nt = min(v - 1, A.enc.n_slots - 1);
-        if (neg) nt = max(nt, 0);
-        desc = A.enc.n_slots - nt - 1;
-        if (desc >= A.enc.n_slots) { status |= DVS_STATUS_SLOT_RANGE; desc = -1; }
-        else atomicAdd(&hist[(neg ? nh : 0) + desc], 1u);
-      }
-      const uint2 rec = make_uint2((uint32_t)(row0 + y) | ((uint32_t)x << 16), rec_word1(a, desc, true));
-      *reinterpret_cast<uint2 *>((i < n_pos ? pos_dst : neg_dst) + i) = rec;
+    int desc;
+    if (ENC == ENC_RATE_CODED) {
+      desc = max(0, (A.enc.n_slots - 1) - (int)__umulhi((unsigned)a, A.enc.dv.magic));  // k, gs:830-832
+      atomicAdd(&hist[(neg ? nh : 0) + desc], 1u);
+    } else {
+      // make_spike_lists_time gs:903-926 (see fast2_tile)
+      const int v = (int)__umulhi((unsigned)a, A.enc.dv.magic);
+      int nt = min(v - 1, A.enc.n_slots - 1);
+      if (neg) nt = max(nt, 0);
+      desc = A.enc.n_slots - nt - 1;
+      if (desc >= A.enc.n_slots) { status |= DVS_STATUS_SLOT_RANGE; desc = -1; }
+      else atomicAdd(&hist[(neg ? nh : 0) + desc], 1u);
     }
+    const uint2 rec = make_uint2((uint32_t)(row0 + y) | ((uint32_t)x << 16), rec_word1(a, desc, true));
+    *reinterpret_cast<uint2 *>((i < n_pos ? pos_dst : neg_dst) + i) = rec;
   }
   if (ENC == ENC_TIME_CODED) {
     status = __reduce_or_sync(kFull, status);
