@@ -21,6 +21,27 @@ namespace dvs {
 
 DEV uint4 ld16_stream(const void *p) { return __ldcs(reinterpret_cast<const uint4 *>(p)); }
 
+// PRMT with the full selector (bit 3 of a selector nibble replicates the sign bit of the chosen byte over the target
+// byte; __byte_perm() ignores that bit, hence the inline PTX)
+template <uint32_t SEL>
+DEV uint32_t prmt(uint32_t a, uint32_t b = 0u) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(SEL));
+  return r;
+}
+// bit 15 / 31 of x replicated over its 16-bit lane (byte 1 -> bytes 0, 1; byte 3 -> bytes 2, 3)
+DEV uint32_t msb_lane_mask(uint32_t x) { return prmt<0xBB99u>(x); }
+// two flag words with bits 15 / 31 (nothing else set in bytes 1 and 3 above bit 7 matters) -> flags of the four
+// pixels as bits 0-3: the four bytes are gathered with one PRMT, their top bits moved to bits 0, 8, 16, 24, and a
+// multiplication lines them up in bits 24-27 (b_k * 2^(8k) * 2^(24 - 7k); all partial products are distinct bits)
+DEV uint32_t flags4_of(uint32_t f_lo, uint32_t f_hi) {
+  const uint32_t g = prmt<0x7531u>(f_lo, f_hi) & 0x80808080u;
+  return ((g >> 7) * 0x01020408u) >> 24;
+}
+// the inverse for four pixel flags in bits 0-3 of n (n < 16): word with the flag of pixel k in bit 8k + 7, from which
+// prmt<0x9988> / prmt<0xBBAA> make the lane masks of the first / second pixel pair
+DEV uint32_t bytes_of_flags4(uint32_t n) { return n * 0x10204080u; }
+
 // shared memory of the fast kernel: [sd: tile_px int16][wl: tile_px uint16][code: tile_px uint8]
 //                                   [wtot: 128 u32][hist: 2 * (n_slots + 1) u32][misc: 8 u32]
 #ifndef FAST2_MINB
@@ -49,6 +70,9 @@ DEV uint4 ld16_stream(const void *p) { return __ldcs(reinterpret_cast<const uint
 #endif
 #ifndef FAST2_QONLY_ADAPT
 #define FAST2_QONLY_ADAPT 0  // index-only work list for the adaptive kernels as well
+#endif
+#ifndef FAST2_THR_EARLY
+#define FAST2_THR_EARLY 1    // adaptive thresholds without inhibition: advanced and stored in the threshold pass itself
 #endif
 constexpr int kFastCap = 2048;  // work-list capacity; denser tiles go to the generic body (redo list)
 
@@ -100,6 +124,10 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   // lane that takes a candidate reads the old threshold from the plane like the frame and reference pixels, and the
   // push stores nothing but the index
   constexpr bool TLATE = ADAPT && QONLY && FAST2_QONLY_ADAPT == 2;
+  // ADAPT without inhibition: a pixel's spike flag is final as soon as it is thresholded, so the new threshold is
+  // computed from the flag word's lane mask (one PRMT) and stored right there; the old thresholds stay in registers
+  // for the candidates' divisions, and a tile that turns out to be declined writes them back before it is handed on
+  constexpr bool THR_EARLY = FAST2_THR_EARLY && ADAPT && !PAIR && !TLATE;
   // 2x2 tiles, static threshold, inlined encoder, int16 frames (the headline kernel): threshold, inhibition and the
   // work-list entry of each area's winner are computed in one pass over the area words while frame and reference are at
   // hand -- the winner's abs_diff, position and sign all come out of one packed key maximum -- so the push after the
@@ -185,6 +213,23 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     const uint32_t f = ADAPT ? ~((t_pk[ADAPT ? j : 0][w] | 0x80008000u) - a) & 0x80008000u : (a + kadd) & 0x80008000u;
     return a & ((f >> 15) * 0xffffu);
   };
+  // update_reference_rate_adpt gs:291-297 on packed lanes: +up on the lanes of m (pixels that still spike), -down
+  // elsewhere, clipped to [min, max]
+  auto thr_new = [&](uint32_t th, uint32_t m) -> uint32_t {
+    const uint32_t up2 = (uint32_t)A.upd.thr_up * 0x00010001u, dn2 = (uint32_t)A.upd.thr_down * 0x00010001u;
+    const uint32_t mn2 = (uint32_t)A.upd.min_thr * 0x00010001u, mx2 = (uint32_t)A.upd.max_thr * 0x00010001u;
+    if (!A.upd.uncoded) {  // (the host admits the coded rule only with up + down <= 32768)
+      // coded rule in a domain biased by `down` (no lane can borrow): x = th + (spike ? up + down : 0) stands for
+      // th + up resp. th - down, clip(x, min + down, max + down) - down is the clipped threshold.  th + up <= 32767
+      // (range vote) and up + down <= 32768 keep every lane below 2^16.
+      return __vminu2(__vmaxu2(th + (m & (up2 + dn2)), mn2 + dn2), mx2 + dn2) - dn2;
+    }
+    // uncoded twin gsu:286-295: += up only while th < max, -= down only while th > min, no clip.
+    // lane-wise compare of values < 2^15: bit 15 of ((x | 0x8000) - y) is set iff x >= y
+    const uint32_t ge_max = msb_lane_mask((th | 0x80008000u) - mx2);  // th >= max
+    const uint32_t le_min = msb_lane_mask((mn2 | 0x80008000u) - th);  // min >= th
+    return th + ((up2 & ~ge_max) & m) - ((dn2 & ~le_min) & ~m);
+  };
   uint32_t wle[FUSED2 ? JH : 1][4];  // FUSED2: finished work-list entry of each area (0 = none)
   if constexpr (FUSED2) {
 #pragma unroll
@@ -235,9 +280,12 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     if (ADAPT) tmax = __vmaxu2(tmax, __vmaxu2(__vmaxu2(t_pk[j][0], t_pk[j][1]), __vmaxu2(t_pk[j][2], t_pk[j][3])));
     rng |= (r_pk[j][0] | r_pk[j][1] | r_pk[j][2]) | r_pk[j][3];
     if (SRC != SRC_U8) rng |= (c_pk[j][0] | c_pk[j][1] | c_pk[j][2]) | c_pk[j][3];
-    if (fl[0] | fl[1] | fl[2] | fl[3]) {
+    if (fl[0] | fl[1] | fl[2] | fl[3]) flags8[j] = flags4_of(fl[0], fl[1]) | (flags4_of(fl[2], fl[3]) << 4);
+    if (THR_EARLY) {
+      uint32_t tn[4];
 #pragma unroll
-      for (int w = 0; w < 4; ++w) flags8[j] |= (((fl[w] >> 15) & 1u) | ((fl[w] >> 30) & 2u)) << (2 * w);
+      for (int w = 0; w < 4; ++w) tn[w] = thr_new(t_pk[ADAPT ? j : 0][w], msb_lane_mask(fl[w]));
+      st16(thr_t + q0_of(j), tn);
     }
   }
   }
@@ -313,55 +361,16 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   // elsewhere, clipped to [min, max]; written back for every pixel.  Deferred until the tile is known to
   // stay in this kernel (a declined tile must reach the generic body with its thresholds untouched).
   auto store_thresholds = [&]() {
-    const uint32_t up2 = (uint32_t)A.upd.thr_up * 0x00010001u, dn2 = (uint32_t)A.upd.thr_down * 0x00010001u;
-    const uint32_t mn2 = (uint32_t)A.upd.min_thr * 0x00010001u, mx2 = (uint32_t)A.upd.max_thr * 0x00010001u;
-    const uint32_t mnd2 = mn2 + dn2;
-    constexpr bool BIASED = FAST2_THR_BIASED == 1 || (FAST2_THR_BIASED == 2 && SRC == SRC_U8);
-    if (BIASED && !A.upd.uncoded) {  // (the host admits the coded rule only with up + down <= 32768)
-      // coded rule in a domain biased by `down` (no lane can borrow): x = th + (spike ? up + down : 0) stands for
-      // th + up resp. th - down, clip(x, min + down, max + down) - down is the clipped threshold.  th + up <= 32767
-      // (range vote) and up + down <= 32768 keep every lane below 2^16.  The 2-bit spike field of a word becomes a lane
-      // mask with two multiplications: ((f >> 2w) * 0x8001) & 0x10001 moves the bits to positions 0 and 16.
-      const uint32_t ud2 = up2 + dn2, mxd2 = mx2 + dn2;
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        if (!have[j]) continue;
-        uint32_t tn[4];
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const uint32_t m = (((flags8[j] >> (2 * w)) * 0x8001u) & 0x10001u) * 0xffffu;
-          tn[w] = __vminu2(__vmaxu2(t_pk[j][w] + (m & ud2), mnd2), mxd2) - dn2;
-        }
-        st16(thr_t + q0_of(j), tn);
-      }
-      return;
-    }
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       if (!have[j]) continue;
+      // lane masks of the four words from the 8 pixel flags: flag k -> bit 8k + 7 of a word (multiplication), then PRMT
+      const uint32_t g01 = bytes_of_flags4(flags8[j] & 0xfu), g23 = bytes_of_flags4(flags8[j] >> 4);
       uint32_t tn[4];
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const uint32_t th = t_pk[j][w];
-        uint32_t t_dn, t_up = 0;
-        if (!BIASED && !A.upd.uncoded) {
-          t_dn = __vminu2(__vmaxu2(th, mnd2) - dn2, mx2);                // clip(th - down, min, max)
-          if (flags8[j]) t_up = __vminu2(__vmaxu2(th + up2, mn2), mx2);  // clip(th + up, min, max); th + up <= 32767 (range vote)
-        } else {
-          // uncoded twin gsu:286-295: += up only while th < max, -= down only while th > min, no clip.
-          // lane-wise compare of values < 2^15: bit 15 of ((x | 0x8000) - y) is set iff x >= y
-          const uint32_t ge_max = ((th | 0x80008000u) - mx2) & 0x80008000u;       // th >= max
-          const uint32_t le_min = ((mn2 | 0x80008000u) - th) & 0x80008000u;       // min >= th
-          t_dn = th - (dn2 & ~((le_min >> 15) * 0xffffu));                        // th - down where th > min
-          if (flags8[j]) t_up = th + (up2 & ~((ge_max >> 15) * 0xffffu));         // th + up where th < max
-        }
-        uint32_t v = t_dn;
-        if (flags8[j]) {
-          const uint32_t m = ((flags8[j] >> (2 * w)) & 1u) * 0xffffu | ((flags8[j] >> (2 * w + 1)) & 1u) * 0xffff0000u;
-          v = (t_up & m) | (t_dn & ~m);
-        }
-        tn[w] = v;
-      }
+      tn[0] = thr_new(t_pk[ADAPT ? j : 0][0], prmt<0x9988u>(g01));
+      tn[1] = thr_new(t_pk[ADAPT ? j : 0][1], prmt<0xBBAAu>(g01));
+      tn[2] = thr_new(t_pk[ADAPT ? j : 0][2], prmt<0x9988u>(g23));
+      tn[3] = thr_new(t_pk[ADAPT ? j : 0][3], prmt<0xBBAAu>(g23));
       st16(thr_t + q0_of(j), tn);
     }
   };
@@ -408,17 +417,22 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   const uint32_t ent = ent_raw & 0x7fffffffu, ent2 = ent_raw2 & 0x7fffffffu;
   const int n_cand = (int)__reduce_add_sync(kFull, ent + ent2);  // redux.sync: the tile's candidate count
   if (n_cand == 0 && !unsafe) {  // quiet tile: no records, no events, reference untouched (unless it decays)
-    if (ADAPT) store_thresholds();
+    if (ADAPT && !THR_EARLY) store_thresholds();
     if (decay) store_decayed_reference();
     for (int c = tid; c < A.C; c += blockDim.x)
       A.tile_counts[((size_t)s_idx * A.C + c) * A.tiles_per_stream + t_idx] = 0;
     return;
   }
   if (unsafe || n_cand > kFastCap) {  // generic body: exact int16 wrap semantics / dense tiles
+    if (THR_EARLY) {  // ... which must find the thresholds as they were
+#pragma unroll
+      for (int j = 0; j < J; ++j)
+        if (have[j]) st16(thr_t + q0_of(j), t_pk[ADAPT ? j : 0]);
+    }
     if (tid == 0) A.redo[1 + atomicAdd(A.redo, 1)] = tile;
     return;
   }
-  if (ADAPT && !TLATE) store_thresholds();
+  if (ADAPT && !TLATE && !THR_EARLY) store_thresholds();
   if (decay) store_decayed_reference();
   {
     // entry: tile-local pixel index (13 bits) | reference << 13 (8 bits) | abs_diff << 21 (8 bits) | negative << 29

@@ -26,14 +26,6 @@ namespace dvs {
 #define FAST2R_MINB 5
 #endif
 
-// bit 15 / 31 of x replicated over its 16-bit lane: one PRMT with sign-replicating selectors (byte 1 -> bytes 0, 1;
-// byte 3 -> bytes 2, 3).  __byte_perm() ignores bit 3 of a selector nibble, hence the inline PTX.
-DEV uint32_t msb_lane_mask(uint32_t x) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(0xBB99u));
-  return r;
-}
-
 template <int SRC, int JH, int ENC>
 DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigned char *smem_raw) {
   static_assert(ENC == ENC_RATE_CODED || ENC == ENC_TIME_CODED, "inlined encoders only");
