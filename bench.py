@@ -470,7 +470,7 @@ class Case:
 
     def launches_per_step(self):
         d = self.dvs
-        return 3 + (1 if d.S * 2 * d.n_slots <= 8192 else 3) + 1   # K1, redo, scan_tiles, segment scan(s), expand
+        return 2 + (1 if d.S * 2 * d.n_slots <= 8192 else 4) + 1   # K1, redo, scan (+ segment scans when many), expand
 
     def timed(self, K, warmup, barrier, sampler=None, split=True):
         """K steps bracketed by CUDA events on the launching stream.  split: per-launch events around K1."""
@@ -946,7 +946,7 @@ def run_ours(args, wl, rank, local_rank, world):
         "config": cfgd,
         "details": {"streams_per_gpu": S, "events_last_step": events_last_step, "frames_per_stream_before_timing": frames_done_timed - K,
                     "pipeline_depth": args.pipeline_depth, "cuda_graph": bool(t["k1_ms"] is None)},
-        "roofline": {"bound": "hbm", "kernel": "K1 fused tile pass (k_tile_fast2 when the fast path applies; timed with its 4-byte memset and the normally empty k_tile_redo launch)",
+        "roofline": {"bound": "hbm", "kernel": "K1 fused tile pass (k_tile_fast2 when the fast path applies; timed with the normally empty k_tile_redo launch)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "frac_of_8tbs_spec": achieved / 8000.0, "bytes_per_px": bpp, "k1_ms": k1_ms,

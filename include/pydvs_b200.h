@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DVS_ABI_VERSION 2
+#define DVS_ABI_VERSION 3
 
 /* error codes (>= 1000 so they cannot collide with cudaError_t) */
 #define DVS_OK 0
@@ -150,8 +150,10 @@ typedef struct dvs_step_params {
   dvs_record *records;      /* S * tiles_per_stream * record_stride records (tile-local lists)  */
   uint32_t *tile_counts;    /* [S][C][tiles_per_stream]                                       */
   int32_t *status;          /* device status word or NULL                                     */
-  int32_t *redo;            /* optional scratch, 1 + S * tiles_per_stream int32: enables the    */
-                            /*   specialised fast kernel (tiles it declines are listed here)    */
+  int32_t *redo;            /* optional scratch, 2 + S * tiles_per_stream int32, the first two  */
+                            /*   words ZERO before the first step (every step leaves them zero):*/
+                            /*   enables the specialised fast kernel (tiles it declines are     */
+                            /*   listed here and replayed by the generic body)                  */
 } dvs_step_params;
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -222,6 +224,13 @@ int dvs_lists_to_tiles(const int16_t *pos, int64_t n_pos, int64_t pos_stride, co
  * global CSR row pointers seg_offsets (last entry = total number of events). */
 int dvs_scan_tiles(int32_t S, int32_t tiles_per_stream, int32_t n_slots, const uint32_t *tile_counts,
                    uint32_t *tile_excl, uint32_t *stream_totals, int64_t *seg_offsets, void *stream);
+/* The same in ONE launch: `ticket` is a device word that is zero before the first call (and left zero); the last
+ * CTA of the tile scan builds seg_offsets.  Falls back to the separate launches when there are more than 8192
+ * (stream, slot, polarity) segments.  Replaces the list concatenation order of make_spike_lists_* (gs:783-1099)
+ * exactly like dvs_scan_tiles. */
+int dvs_scan_tiles_ticket(int32_t S, int32_t tiles_per_stream, int32_t n_slots, const uint32_t *tile_counts,
+                          uint32_t *tile_excl, uint32_t *stream_totals, int64_t *seg_offsets, uint32_t *ticket,
+                          void *stream);
 
 /* K3: expand tile-local records into AER events at their final CSR positions (make_spike_lists_*).
  * tile_px = records per tile region (tile_rows * W, or `chunk`).  If the total exceeds event_cap

@@ -18,7 +18,7 @@ POL_UP, POL_DOWN, POL_MERGED, POL_RECTIFIED = 0, 1, 2, 3
 UPD_RATE, UPD_RATE_ADPT, UPD_TIME_BIN_RAW, UPD_TIME_BIN_THR, UPD_NONE = 0, 1, 2, 3, 4
 ENC_RATE, ENC_TIME, ENC_TIME_BIN, ENC_TIME_BIN_THR, ENC_NONE = 0, 1, 2, 3, 4
 FRAME_I16, FRAME_U8 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 PATH_GENERIC, PATH_FAST, PATH_FAST_4X4 = 0, 1, 2
 
 
@@ -93,6 +93,7 @@ _SIGNATURES = {
     "dvs_lists_to_tiles": (C.c_int, [_P, _I64, _I64, _P, _I64, _I64, _I32, C.POINTER(EncParams), _P, _P,
                                      _P, _P]),
     "dvs_scan_tiles": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "dvs_scan_tiles_ticket": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "dvs_aer_expand": (C.c_int, [_I32, _I32, _I32, C.POINTER(EncParams), _P, _P, _P, _P, _P, _I64, _P,
                                  _P]),
     "dvs_gather_split": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _I64, _P, _I64, _P]),

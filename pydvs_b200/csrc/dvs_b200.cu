@@ -88,62 +88,28 @@ __global__ void __launch_bounds__(256) k_lists_to_tiles(const __grid_constant__ 
 // ================================================================================================
 // K2: scans
 // ================================================================================================
-// one warp per (stream, component): exclusive scan over the stream's tiles (contiguous memory)
-__global__ void __launch_bounds__(256) k_scan_tiles(int n_rows, int tps, const uint32_t *__restrict__ counts,
-                                                    uint32_t *__restrict__ excl,
-                                                    uint32_t *__restrict__ totals) {
-  const int gw = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (gw >= n_rows) return;
-  const size_t base = (size_t)gw * tps;
-  uint32_t carry = 0;
-  // 256 tiles per pass: the eight loads of a lane are independent and in flight together (a warp walking its row 32
-  // tiles at a time pays one DRAM / L2 latency per step of the carry chain: 34 of them for a 4K stream)
-  for (int t0 = 0; t0 < tps; t0 += 256) {
-    uint32_t v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int t = t0 + u * 32 + lane;
-      v[u] = t < tps ? counts[base + t] : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int t = t0 + u * 32 + lane;
-      uint32_t x = v[u];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(kFull, x, o);
-        if (lane >= o) x += y;
-      }
-      if (t < tps) excl[base + t] = carry + x - v[u];
-      carry += __shfl_sync(kFull, x, 31);
-    }
-  }
-  if (lane == 0) totals[gw] = carry;
-}
-
-// single CTA: CSR row pointers over (stream, slot, polarity) from the stream totals.  A thread owns whole
-// streams (a contiguous run of them), so neighbouring threads read neighbouring rows of `totals` and no
-// index arithmetic beyond two nested loops is needed.
-__global__ void __launch_bounds__(1024) k_scan_segments(int S, int n_slots, const uint32_t *__restrict__ totals,
-                                                        long long *__restrict__ seg_offsets) {
+// CSR row pointers over (stream, slot, polarity) from the stream totals, by ONE CTA: the S * 2 * n_slots segments are
+// cut into one contiguous run per thread (segment k = words 2.. of row k / per of `totals`), so every thread of the
+// CTA has work even for a few streams and its loads are in flight together.  The totals may have been written by other
+// CTAs of the same launch (the tile scan's last block): they are read past L1 (ld.cg).
+DEV void seg_scan_block(int S, int n_slots, const uint32_t *totals, long long *seg_offsets) {
   __shared__ long long wsum[32];
   __shared__ long long carry_sm;
   const int C = 2 + 2 * n_slots, per = 2 * n_slots;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int chunk = (S + (int)blockDim.x - 1) / (int)blockDim.x;
-  const int lo = min(S, tid * chunk), hi = min(S, lo + chunk);
-  // the thread's rows are one contiguous run of words: walk it flat and unrolled so that eight loads are in
-  // flight at a time (a single CTA is latency-bound otherwise); the first two words of a row are not slots
-  const uint32_t *base = totals + (long long)lo * C;
-  const int n_words = (hi - lo) * C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = (int)blockDim.x >> 5;
+  const int n_seg = S * per;  // <= 8192 (host-checked)
+  const int chunk = (n_seg + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int lo = min(n_seg, tid * chunk), hi = min(n_seg, lo + chunk);
+  const int row0 = lo / per, col0 = lo - row0 * per;
   long long sum = 0;
   {
-    int c = 0;
+    const uint32_t *p = totals + (long long)row0 * C + 2 + col0;
+    int c = col0;
 #pragma unroll 8
-    for (int i = 0; i < n_words; ++i) {
-      const uint32_t v = base[i];
-      if (c >= 2) sum += v;
-      if (++c == C) c = 0;
+    for (int k = lo; k < hi; ++k) {
+      sum += __ldcg(p);
+      ++p;
+      if (++c == per) { c = 0; p += 2; }
     }
   }
   long long x = sum;
@@ -155,7 +121,7 @@ __global__ void __launch_bounds__(1024) k_scan_segments(int S, int n_slots, cons
   if (lane == 31) wsum[warp] = x;
   __syncthreads();
   if (warp == 0) {
-    long long w = wsum[lane], wx = w;
+    long long w = lane < n_warps ? wsum[lane] : 0, wx = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const long long y = __shfl_up_sync(kFull, wx, o);
@@ -167,19 +133,145 @@ __global__ void __launch_bounds__(1024) k_scan_segments(int S, int n_slots, cons
   __syncthreads();
   long long run = wsum[warp] + x - sum;
   {
-    long long *out = seg_offsets + (long long)lo * per;
-    int c = 0;
+    const uint32_t *p = totals + (long long)row0 * C + 2 + col0;
+    int c = col0;
 #pragma unroll 8
-    for (int i = 0; i < n_words; ++i) {
-      const uint32_t v = base[i];
-      if (c >= 2) {
-        *out++ = run;
-        run += v;
-      }
-      if (++c == C) c = 0;
+    for (int k = lo; k < hi; ++k) {
+      seg_offsets[k] = run;
+      run += __ldcg(p);
+      ++p;
+      if (++c == per) { c = 0; p += 2; }
     }
   }
-  if (tid == 0) seg_offsets[(long long)S * per] = carry_sm;
+  if (tid == 0) seg_offsets[n_seg] = carry_sm;
+}
+
+// one warp per (stream, component): exclusive scan over the stream's tiles (contiguous memory).  With a `ticket`
+// (one zero word, left zero) the last CTA to finish also builds the CSR row pointers (seg_scan_block), which saves
+// the separate single-CTA launch: at 32 streams per GPU the two scans were 14 us of a 250 us step.
+__global__ void __launch_bounds__(256) k_scan_tiles(int n_rows, int tps, const uint32_t *__restrict__ counts,
+                                                    uint32_t *__restrict__ excl, uint32_t *totals, int S, int n_slots,
+                                                    long long *seg_offsets, unsigned *ticket) {
+  const int gw = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
+  if (gw < n_rows) {
+    const size_t base = (size_t)gw * tps;
+    uint32_t carry = 0;
+    // 256 tiles per pass: the eight loads of a lane are independent and in flight together, and the loads of the next
+    // pass are issued before the current one is scanned (the counters of a large step have left L2 by now: a warp
+    // that waits for each pass pays one DRAM latency per 256 tiles, five of them for a 4K stream)
+    uint32_t v[8], nx[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int t = u * 32 + lane;
+      v[u] = t < tps ? counts[base + t] : 0;
+    }
+    for (int t0 = 0; t0 < tps; t0 += 256) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int t = t0 + 256 + u * 32 + lane;
+        nx[u] = t < tps ? counts[base + t] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int t = t0 + u * 32 + lane;
+        uint32_t x = v[u];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(kFull, x, o);
+          if (lane >= o) x += y;
+        }
+        if (t < tps) excl[base + t] = carry + x - v[u];
+        carry += __shfl_sync(kFull, x, 31);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = nx[u];
+    }
+    if (lane == 0) totals[gw] = carry;
+  }
+  if (ticket == nullptr) return;
+  __shared__ int is_last;
+  __syncthreads();  // every warp of this CTA has written its totals
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *ticket = 0u;
+  seg_scan_block(S, n_slots, totals, seg_offsets);
+}
+
+// The same scan with one CTA (256 threads) per (stream, component) row, for rows of more than 256 tiles: all loads of
+// a row (up to 2048 tiles per round) are in flight at once and the 8 x 8 (pass, warp) totals meet in shared memory
+// behind a single barrier, instead of one warp walking the row pass by pass (4K streams: 1080 tiles per row; at 32
+// streams per GPU the warp-per-row form took 9.6 us, as long as 5 % of the step).
+__global__ void __launch_bounds__(256) k_scan_tiles_wide(int tps, const uint32_t *__restrict__ counts,
+                                                         uint32_t *__restrict__ excl, uint32_t *totals, int S, int n_slots,
+                                                         long long *seg_offsets, unsigned *ticket) {
+  __shared__ uint32_t wt[64];
+  __shared__ int is_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t base = (size_t)blockIdx.x * tps;
+  uint32_t carry = 0;
+  pdl_trigger();
+  pdl_wait();
+  for (int t0 = 0; t0 < tps; t0 += 2048) {
+    uint32_t v[8], x[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int t = t0 + p * 256 + tid;
+      v[p] = t < tps ? counts[base + t] : 0u;
+    }
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      x[p] = v[p];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(kFull, x[p], o);
+        if (lane >= o) x[p] += y;
+      }
+      if (lane == 31) wt[p * 8 + warp] = x[p];
+    }
+    __syncthreads();
+    // exclusive scan of the 64 (pass, warp) totals, redundantly by every warp: lane l holds entries l and l + 32
+    const uint32_t w0 = wt[lane], w1 = wt[lane + 32];
+    uint32_t s0 = w0, s1 = w1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y0 = __shfl_up_sync(kFull, s0, o), y1 = __shfl_up_sync(kFull, s1, o);
+      if (lane >= o) { s0 += y0; s1 += y1; }
+    }
+    const uint32_t half = __shfl_sync(kFull, s0, 31);
+    const uint32_t e0 = s0 - w0, e1 = s1 - w1 + half;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int k = p * 8 + warp;  // uniform over the warp
+      const uint32_t off = __shfl_sync(kFull, p < 4 ? e0 : e1, k & 31);
+      const int t = t0 + p * 256 + tid;
+      if (t < tps) excl[base + t] = carry + off + x[p] - v[p];
+    }
+    carry += half + __shfl_sync(kFull, s1, 31);
+    __syncthreads();  // wt is rewritten by the next round
+  }
+  if (tid == 0) totals[blockIdx.x] = carry;
+  if (ticket == nullptr) return;
+  if (tid == 0) {
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (tid == 0) *ticket = 0u;
+  seg_scan_block(S, n_slots, totals, seg_offsets);
+}
+
+// single CTA: the row pointers as a launch of their own (dvs_scan_tiles without a ticket)
+__global__ void __launch_bounds__(1024) k_scan_segments(int S, int n_slots, const uint32_t *totals, long long *seg_offsets) {
+  seg_scan_block(S, n_slots, totals, seg_offsets);
 }
 
 // Many streams (S * 2 * n_slots > 8192 segments): a single CTA would have to pull megabytes through one SM.
@@ -272,6 +364,7 @@ struct ExpandArgs {
 // current one is expanded, so the dependent-load chain per task is off the critical path.
 template <bool NS8>
 __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ ExpandArgs A) {
+  pdl_wait();  // the scan (and through it the tile pass) has completed
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.y;
   // A.tpw tasks per warp (32 when there are plenty of tiles, fewer to keep >= ~16k warps in flight)
@@ -1031,8 +1124,8 @@ int dvs_lists_to_tiles(const int16_t *pos, int64_t n_pos, int64_t pos_stride, co
   return check_launch("k_lists_to_tiles");
 }
 
-int dvs_scan_tiles(int32_t S, int32_t tiles_per_stream, int32_t n_slots, const uint32_t *tile_counts,
-                   uint32_t *tile_excl, uint32_t *stream_totals, int64_t *seg_offsets, void *stream) {
+static int scan_tiles_impl(int32_t S, int32_t tiles_per_stream, int32_t n_slots, const uint32_t *tile_counts,
+                           uint32_t *tile_excl, uint32_t *stream_totals, int64_t *seg_offsets, uint32_t *ticket, void *stream) {
   if (S <= 0 || tiles_per_stream <= 0 || n_slots < 0 || n_slots > kMaxSlots || !tile_counts || !tile_excl ||
       !stream_totals)
     return fail(DVS_ERR_INVALID_ARGUMENT, "scan_tiles arguments");
@@ -1040,17 +1133,31 @@ int dvs_scan_tiles(int32_t S, int32_t tiles_per_stream, int32_t n_slots, const u
   const long long n_rows = (long long)S * C;
   if (n_rows > 0x7fffffffll / 32) return fail(DVS_ERR_UNSUPPORTED, "S * C too large");
   const unsigned grid = (unsigned)((n_rows * 32 + 255) / 256);
-  k_scan_tiles<<<grid, 256, 0, as_stream(stream)>>>((int)n_rows, tiles_per_stream, tile_counts, tile_excl, stream_totals);
+  long long *seg = reinterpret_cast<long long *>(seg_offsets);
+  const bool small = (long long)S * 2 * n_slots <= 8192;
+  const bool fused = ticket && seg && n_slots > 0 && small;  // the last CTA of the tile scan builds the row pointers
+  // (const / non-const copies of the arguments so that cudaLaunchKernelEx sees the kernels' exact parameter types)
+  const uint32_t *counts_c = tile_counts;
+  long long *seg_k = fused ? seg : nullptr;
+  unsigned *ticket_k = fused ? ticket : nullptr;
+  int tps_k = tiles_per_stream, S_k = S, ns_k = n_slots, rows_k = (int)n_rows;
+  cudaError_t le;
+  if (tiles_per_stream > 256 && n_rows <= 0x7fffffffll / 256)
+    le = launch_pdl(k_scan_tiles_wide, dim3((unsigned)n_rows), dim3(256), 0, as_stream(stream), tps_k, counts_c, tile_excl,
+                    stream_totals, S_k, ns_k, seg_k, ticket_k);
+  else
+    le = launch_pdl(k_scan_tiles, dim3(grid), dim3(256), 0, as_stream(stream), rows_k, tps_k, counts_c, tile_excl, stream_totals,
+                    S_k, ns_k, seg_k, ticket_k);
+  if (le != cudaSuccess) return fail((int)le, cudaGetErrorString(le));
   int rc = check_launch("k_scan_tiles");
-  if (rc) return rc;
+  if (rc || fused) return rc;
   if (seg_offsets) {
     if (n_slots == 0) {
       cudaError_t e = cudaMemsetAsync(seg_offsets, 0, sizeof(int64_t), as_stream(stream));
       if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
       return DVS_OK;
     }
-    long long *seg = reinterpret_cast<long long *>(seg_offsets);
-    if ((long long)S * 2 * n_slots <= 8192) {
+    if (small) {
       k_scan_segments<<<1, 1024, 0, as_stream(stream)>>>(S, n_slots, stream_totals, seg);
     } else {
       const unsigned blocks = (unsigned)((S + 127) / 128);
@@ -1061,6 +1168,17 @@ int dvs_scan_tiles(int32_t S, int32_t tiles_per_stream, int32_t n_slots, const u
     rc = check_launch("k_scan_segments");
   }
   return rc;
+}
+
+int dvs_scan_tiles(int32_t S, int32_t tiles_per_stream, int32_t n_slots, const uint32_t *tile_counts,
+                   uint32_t *tile_excl, uint32_t *stream_totals, int64_t *seg_offsets, void *stream) {
+  return scan_tiles_impl(S, tiles_per_stream, n_slots, tile_counts, tile_excl, stream_totals, seg_offsets, nullptr, stream);
+}
+
+int dvs_scan_tiles_ticket(int32_t S, int32_t tiles_per_stream, int32_t n_slots, const uint32_t *tile_counts,
+                          uint32_t *tile_excl, uint32_t *stream_totals, int64_t *seg_offsets, uint32_t *ticket,
+                          void *stream) {
+  return scan_tiles_impl(S, tiles_per_stream, n_slots, tile_counts, tile_excl, stream_totals, seg_offsets, ticket, stream);
 }
 
 int dvs_aer_expand(int32_t S, int32_t tiles_per_stream, int32_t tile_px, const dvs_enc_params *enc,
@@ -1084,8 +1202,9 @@ int dvs_aer_expand(int32_t S, int32_t tiles_per_stream, int32_t tile_px, const d
   const int tasks_per_block = 8 * tpw;
   const dim3 grid((unsigned)((2 * tiles_per_stream + tasks_per_block - 1) / tasks_per_block), (unsigned)S);
   const bool ns8 = (A.enc.mode == DVS_ENC_RATE || A.enc.mode == DVS_ENC_TIME) && A.enc.n_slots <= 8;
-  if (ns8) k_expand<true><<<grid, 256, 0, as_stream(stream)>>>(A);
-  else k_expand<false><<<grid, 256, 0, as_stream(stream)>>>(A);
+  const cudaError_t le = ns8 ? launch_pdl(k_expand<true>, grid, dim3(256), 0, as_stream(stream), A)
+                             : launch_pdl(k_expand<false>, grid, dim3(256), 0, as_stream(stream), A);
+  if (le != cudaSuccess) return fail((int)le, cudaGetErrorString(le));
   return check_launch("k_expand");
 }
 

@@ -18,6 +18,24 @@ constexpr int kMaxTilePx = 32768;  // 16-bit packed per-tile counters
 constexpr int kMaxSlots = 1024;
 constexpr unsigned kFull = 0xffffffffu;
 
+// Programmatic dependent launch (sm_90+): the small kernels that follow K1 in a step (redo, scan, expand) are
+// launched with the programmatic-stream-serialization attribute, so their CTAs are set up while the previous kernel
+// drains; pdl_wait() then blocks until that kernel has completed and its writes are visible (a no-op for a normal
+// launch).  pdl_trigger() lets the NEXT kernel start that early set-up.  Stream order is unchanged.
+#ifndef DVS_PDL
+#define DVS_PDL 1
+#endif
+DEV void pdl_wait() {
+#if DVS_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+DEV void pdl_trigger() {
+#if DVS_PDL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 DEV int w16(int x) { return (int)(short)x; }
 
 // NumPy floor_divide for int16 operands, exact for |a|, |b| <= 32768: the correctly rounded fp32

@@ -429,7 +429,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       for (int j = 0; j < J; ++j)
         if (have[j]) st16(thr_t + q0_of(j), t_pk[ADAPT ? j : 0]);
     }
-    if (tid == 0) A.redo[1 + atomicAdd(A.redo, 1)] = tile;
+    if (tid == 0) A.redo[2 + atomicAdd(A.redo, 1)] = tile;
     return;
   }
   if (ADAPT && !TLATE && !THR_EARLY) store_thresholds();
@@ -652,6 +652,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
 template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT = false>
 __global__ void __launch_bounds__(256, ADAPT ? FAST2_MINB_ADPT : FAST2_MINB) k_tile_fast2(const __grid_constant__ TileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_trigger();
   fast2_tile<SRC, JH, PAIR, ENC, ADAPT, false>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + kFastCap * 12,
                                                   nullptr, nullptr);
 }
@@ -660,6 +661,7 @@ __global__ void __launch_bounds__(256, ADAPT ? FAST2_MINB_ADPT : FAST2_MINB) k_t
 template <int SRC, int ENC, bool ADAPT, int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 4 : 2) k_tile_fast4(const __grid_constant__ TileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_trigger();
   fast2_tile<SRC, 1, true, ENC, ADAPT, false, true>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + kFastCap * 12,
                                                      nullptr, nullptr);
 }
@@ -703,6 +705,7 @@ DEV void mbar_wait(uint64_t *bar, uint32_t parity) {
 template <int SRC, int JH, bool PAIR, int ENC>
 __global__ void __launch_bounds__(256, FAST2S_MINB) k_tile_fast2s(const __grid_constant__ TileArgs A, const int stage_bytes) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  pdl_trigger();
   unsigned char *ctl = smem_raw + 2 * stage_bytes;
   const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
   uint64_t *bars = reinterpret_cast<uint64_t *>(ctl + (((128 + 2 * nh + 8) * 4 + 256 + 15) & ~15));
@@ -754,7 +757,6 @@ static int launch_fast2(const TileArgs &A_in, int bd, cudaStream_t st) {
   cudaError_t e;
   if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
     return set_error((int)e, cudaGetErrorString(e));
-  if ((e = cudaMemsetAsync(A.redo, 0, sizeof(int32_t), st)) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
   const long long tiles = (long long)A.S * A.tiles_per_stream;
   bool staged = false;
   if constexpr (!ADAPT && PAIR && ENC != ENC_TIME_CODED) {
@@ -787,8 +789,8 @@ static int launch_fast2(const TileArgs &A_in, int bd, cudaStream_t st) {
     return set_error((int)e, cudaGetErrorString(e));
   const int items = A.tile_px / 8;
   const int bd_r = JR == 1 ? (items + 31) / 32 * 32 : ((items + 3) / 4 + 31) / 32 * 32;
-  kr<<<(unsigned)(tiles < 592 ? tiles : 592), bd_r, smem_r, st>>>(A);
-  if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+  e = launch_pdl(kr, dim3((unsigned)(tiles < 592 ? tiles : 592)), dim3((unsigned)bd_r), smem_r, st, A);
+  if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
   return DVS_OK;
 }
 
@@ -799,7 +801,6 @@ static int launch_fast4(const TileArgs &A_in, cudaStream_t st) {
   const int nh = A.enc.n_slots + 1;
   const size_t smem = kFastCap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t) + (ADAPT ? kFastCap * 2 : 0) + 256;
   cudaError_t e;
-  if ((e = cudaMemsetAsync(A.redo, 0, sizeof(int32_t), st)) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
   const int gpr = A.W / 8, bd = (gpr + 31) / 32 * 32;
   const dim3 grid((unsigned)A.tiles_per_stream, (unsigned)A.S);
   if (bd <= 256) {
@@ -821,8 +822,8 @@ static int launch_fast4(const TileArgs &A_in, cudaStream_t st) {
     return set_error((int)e, cudaGetErrorString(e));
   const int items = A.tile_px / 8;
   const long long tiles = (long long)A.S * A.tiles_per_stream;
-  kr<<<(unsigned)(tiles < 296 ? tiles : 296), ((items + 3) / 4 + 31) / 32 * 32, smem_r, st>>>(A);
-  if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+  e = launch_pdl(kr, dim3((unsigned)(tiles < 296 ? tiles : 296)), dim3((unsigned)(((items + 3) / 4 + 31) / 32 * 32)), smem_r, st, A);
+  if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
   return DVS_OK;
 }
 

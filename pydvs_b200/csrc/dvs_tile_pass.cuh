@@ -3,6 +3,8 @@
 #pragma once
 #include <limits.h>
 
+#include <utility>
+
 #include "dvs_device.cuh"
 
 #ifndef GENERIC_J1
@@ -37,7 +39,7 @@ struct TileArgs {
   uint32_t *tile_counts;
   int32_t *status;
   int32_t *global_max;     // [S][2] (pos list, neg list), SRC_PLANES only; INT_MIN = empty
-  int32_t *redo;           // [1 + tiles]: tiles the fast kernel hands to the generic body
+  int32_t *redo;           // [2 + tiles]: count, CTA ticket, tiles the fast kernel hands to the generic body
 };
 
 DEV uint4 ld16(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
@@ -428,23 +430,47 @@ DEV void tile_body(const TileArgs &A, const int tile) {
 
 template <int SRC, int J, int BDMAX, bool ADAPT, int KI>
 __global__ void __launch_bounds__(BDMAX) k_tile_pass(const __grid_constant__ TileArgs A) {
+  pdl_trigger();
   tile_body<SRC, J, ADAPT, KI>(A, blockIdx.x);
 }
 
 // Generic body over the tiles the fast kernel declined (pixels outside [0, 255]): A.redo[0] = count,
-// A.redo[1..] = tile indices.  Launched after every fast pass; normally finds count == 0.
+// A.redo[2..] = tile indices.  Launched after every fast pass; normally finds count == 0.  The last CTA to finish
+// (A.redo[1] counts them) zeroes both words again, so the list is ready for the next step without a memset launch.
 template <int SRC, int J, int KI, bool ADAPT = false, int BDMAX = 256>
 __global__ void __launch_bounds__(BDMAX) k_tile_redo(const __grid_constant__ TileArgs A) {
+  pdl_trigger();
+  pdl_wait();  // the fast pass has completed: its redo list and everything it wrote are visible
   const int n = A.redo[0];
   for (int i = blockIdx.x; i < n; i += gridDim.x) {
-    tile_body<SRC, J, ADAPT, KI>(A, A.redo[1 + i]);
+    tile_body<SRC, J, ADAPT, KI>(A, A.redo[2 + i]);
     __syncthreads();  // shared memory is reused by the next tile
+  }
+  if (n != 0 && threadIdx.x == 0) {  // (n == 0: nothing to reset, and every CTA sees the same n)
+    __threadfence();
+    if (atomicAdd(&A.redo[1], 1) == (int)gridDim.x - 1) {
+      A.redo[1] = 0;
+      A.redo[0] = 0;
+    }
   }
 }
 
 
 // ---- host side ---------------------------------------------------------------------------------
 int set_error(int code, const char *msg);  // dvs_b200.cu: stores the thread-local message, returns code
+
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait() in dvs_device.cuh); the kernel must call
+// pdl_wait() before it touches anything the previous kernel of the stream wrote.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = DVS_PDL;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // Tile shapes: <= 256 groups of 8 px -> one group per thread; <= 1024 groups -> four per thread in
 // CTAs of <= 256 threads; larger tiles (W * inh_k > 8192) only exist in the generic-inhibition

@@ -155,7 +155,7 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
     return;
   }
   if (unsafe) {  // a pixel outside [0, 255]: the generic body replays the tile with exact int16 wrap semantics
-    if (tid == 0) A.redo[1 + atomicAdd(A.redo, 1)] = tile;
+    if (tid == 0) A.redo[2 + atomicAdd(A.redo, 1)] = tile;
     return;
   }
   const unsigned magic = A.upd.div_thr.magic;
@@ -245,6 +245,7 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
 template <int SRC, int JH, int ENC>
 __global__ void __launch_bounds__(256, FAST2R_MINB) k_tile_ranked(const __grid_constant__ TileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_trigger();
   fast2r_tile<SRC, JH, ENC>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw);
 }
 
@@ -258,7 +259,6 @@ static int launch_ranked(const TileArgs &A_in, int bd, cudaStream_t st) {
   const int nh = A.enc.n_slots + 1;
   const size_t smem = kFastCap * 4 + (32 + 2 * nh + 4) * sizeof(uint32_t);
   cudaError_t e;
-  if ((e = cudaMemsetAsync(A.redo, 0, sizeof(int32_t), st)) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
   k_tile_ranked<SRC, JH, ENC><<<dim3((unsigned)A.tiles_per_stream, (unsigned)A.S), bd, smem, st>>>(A);
   if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
   // generic body over the (normally zero) declined tiles
@@ -268,8 +268,8 @@ static int launch_ranked(const TileArgs &A_in, int bd, cudaStream_t st) {
     return set_error((int)e, cudaGetErrorString(e));
   const int items = A.tile_px / 8;
   const long long tiles = (long long)A.S * A.tiles_per_stream;
-  kr<<<(unsigned)(tiles < 592 ? tiles : 592), ((items + 3) / 4 + 31) / 32 * 32, smem_r, st>>>(A);
-  if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+  e = launch_pdl(kr, dim3((unsigned)(tiles < 592 ? tiles : 592)), dim3((unsigned)(((items + 3) / 4 + 31) / 32 * 32)), smem_r, st, A);
+  if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
   return DVS_OK;
 }
 

@@ -233,13 +233,14 @@ class DVSStreams:
                     "tile_counts": counts, "tile_excl": torch.zeros_like(counts),
                     "stream_totals": torch.zeros(self.S * self.C, dtype=torch.int32, device=dev),
                     "seg_offsets": torch.zeros(self.S * self.n_slots * 2 + 1, dtype=torch.int64, device=dev),
+                    "ticket": torch.zeros(1, dtype=torch.int32, device=dev),
                     "events": torch.empty(self.event_capacity, dtype=torch.int64, device=dev), "k3_done": None}
 
         self._sets = [make_set() for _ in range(self.pipeline_depth)]
         self._cur = 0
         self._side = torch.cuda.Stream(device=dev) if self.pipeline_depth > 1 else None
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.redo = torch.zeros(1 + n_tiles, dtype=torch.int32, device=dev)
+        self.redo = torch.zeros(2 + n_tiles, dtype=torch.int32, device=dev)   # count, CTA ticket, declined tiles
         self.debug = None
         if debug_planes:
             self.debug = {n: torch.zeros((self.S, self.H, self.W), dtype=torch.int16, device=dev)
@@ -382,9 +383,11 @@ class DVSStreams:
         self.kernel_path = lib.dvs_last_step_path()   # _lib.PATH_*: which tile kernel ran (generic body or a fast path)
 
     def scan(self):
-        """K2: per-tile counters -> exclusive prefixes and CSR row pointers (two small launches)."""
-        check(lib.dvs_scan_tiles(self.S, self.tps, self.n_slots, _ptr(self.tile_counts), _ptr(self.tile_excl),
-                                 _ptr(self.stream_totals), _ptr(self.seg_offsets), current_stream_ptr()))
+        """K2: per-tile counters -> exclusive prefixes and CSR row pointers (one launch: the last CTA of the tile scan
+        builds the row pointers)."""
+        check(lib.dvs_scan_tiles_ticket(self.S, self.tps, self.n_slots, _ptr(self.tile_counts), _ptr(self.tile_excl),
+                                        _ptr(self.stream_totals), _ptr(self.seg_offsets),
+                                        _ptr(self._sets[self._cur]["ticket"]), current_stream_ptr()))
 
     # -- CUDA-graph replay for launch-bound (small) configurations ---------------------------------
     def capture(self, frames: torch.Tensor):

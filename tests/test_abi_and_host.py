@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), "libpydvs_b200.so does not export %s" % n
     assert set(_lib.EXPORTS) == set(names), "ctypes binding and header disagree"
-    assert _lib.lib.dvs_abi_version() == _lib.ABI_VERSION == 2
+    assert _lib.lib.dvs_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_the_header():
