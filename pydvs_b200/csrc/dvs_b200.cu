@@ -11,6 +11,8 @@
 //   plus the unfused 1:1 kernels behind the drop-in module functions and the float32 DVSOperator mode.
 // Everything is HBM-bound integer work: no tensor cores, no TMEM.
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <limits.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -290,15 +292,17 @@ __global__ void __launch_bounds__(128) k_seg_stream_sums(int S, int n_slots, con
   seg_offsets[(long long)s * per] = sum;
 }
 
-__global__ void __launch_bounds__(1024) k_seg_scan_streams(int S, int per, long long *__restrict__ seg_offsets) {
+// exclusive scan, in place, of the per-stream event totals parked in seg_offsets[s * per], by one CTA (the values may
+// have been written by other CTAs of the same launch: read past L1)
+DEV void seg_scan_streams_block(int S, int per, long long *seg_offsets) {
   __shared__ long long wsum[32];
   __shared__ long long carry_sm;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = (int)blockDim.x >> 5;
   const int chunk = (S + (int)blockDim.x - 1) / (int)blockDim.x;
   const int lo = min(S, tid * chunk), hi = min(S, lo + chunk);
   long long sum = 0;
-#pragma unroll 4
-  for (int s = lo; s < hi; ++s) sum += seg_offsets[(long long)s * per];
+#pragma unroll 16
+  for (int s = lo; s < hi; ++s) sum += __ldcg(seg_offsets + (long long)s * per);
   long long x = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(1024) k_seg_scan_streams(int S, int per, long 
   if (lane == 31) wsum[warp] = x;
   __syncthreads();
   if (warp == 0) {
-    long long w = wsum[lane], wx = w;
+    long long w = lane < n_warps ? wsum[lane] : 0, wx = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const long long y = __shfl_up_sync(kFull, wx, o);
@@ -319,12 +323,62 @@ __global__ void __launch_bounds__(1024) k_seg_scan_streams(int S, int per, long 
   }
   __syncthreads();
   long long run = wsum[warp] + x - sum;
+#pragma unroll 16
   for (int s = lo; s < hi; ++s) {
-    const long long v = seg_offsets[(long long)s * per];
+    const long long v = __ldcg(seg_offsets + (long long)s * per);
     seg_offsets[(long long)s * per] = run;
     run += v;
   }
   if (tid == 0) seg_offsets[(long long)S * per] = carry_sm;
+}
+
+__global__ void __launch_bounds__(1024) k_seg_scan_streams(int S, int per, long long *seg_offsets) {
+  seg_scan_streams_block(S, per, seg_offsets);
+}
+
+// Streams of a few tiles each (tps <= 8: e.g. 4096 MNIST-sized streams of one tile): one warp per STREAM, a lane per
+// component walks the row's tiles; the warp also sums the stream's events.  mode 1: the last CTA builds all row
+// pointers (few segments); mode 2: the stream sums are parked in seg_offsets[s * per] and the last CTA scans them in
+// place (k_seg_fill completes the rows); mode 3: sums parked only; mode 0: no row pointers wanted.
+__global__ void __launch_bounds__(256) k_scan_small(int S, int tps, int n_slots, const uint32_t *__restrict__ counts,
+                                                    uint32_t *__restrict__ excl, uint32_t *totals, long long *seg_offsets,
+                                                    unsigned *ticket, int mode) {
+  const int s = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int C = 2 + 2 * n_slots;
+  pdl_trigger();
+  pdl_wait();
+  if (s < S) {
+    unsigned long long events = 0;
+    for (int c = lane; c < C; c += 32) {
+      const size_t base = ((size_t)s * C + c) * tps;
+      uint32_t run = 0;
+      for (int t = 0; t < tps; ++t) {
+        const uint32_t v = counts[base + t];
+        excl[base + t] = run;
+        run += v;
+      }
+      totals[(size_t)s * C + c] = run;
+      if (c >= 2) events += run;
+    }
+    if (mode >= 2) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) events += __shfl_xor_sync(kFull, events, o);
+      if (lane == 0) seg_offsets[(long long)s * 2 * n_slots] = (long long)events;
+    }
+  }
+  if (mode == 0 || mode == 3) return;
+  __shared__ int is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *ticket = 0u;
+  if (mode == 1) seg_scan_block(S, n_slots, totals, seg_offsets);
+  else seg_scan_streams_block(S, 2 * n_slots, seg_offsets);
 }
 
 __global__ void __launch_bounds__(128) k_seg_fill(int S, int n_slots, const uint32_t *__restrict__ totals,
@@ -561,7 +615,7 @@ __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ ExpandAr
           const int m = enc_mult(A.enc, desc, sb + jj, sm);
           const long long b = __shfl_sync(kFull, base, jj);
           int tot, ex;
-          if (!bin_mode) {
+          if (!bin_mode || !__any_sync(kFull, m > 1)) {  // (time-binary: multiplicities above 1 only when a value wraps)
             const unsigned bal = __ballot_sync(kFull, m != 0);
             tot = __popc(bal);
             ex = __popc(bal & lt);
@@ -1142,15 +1196,36 @@ static int scan_tiles_impl(int32_t S, int32_t tiles_per_stream, int32_t n_slots,
   unsigned *ticket_k = fused ? ticket : nullptr;
   int tps_k = tiles_per_stream, S_k = S, ns_k = n_slots, rows_k = (int)n_rows;
   cudaError_t le;
-  if (tiles_per_stream > 256 && n_rows <= 0x7fffffffll / 256)
-    le = launch_pdl(k_scan_tiles_wide, dim3((unsigned)n_rows), dim3(256), 0, as_stream(stream), tps_k, counts_c, tile_excl,
-                    stream_totals, S_k, ns_k, seg_k, ticket_k);
-  else
-    le = launch_pdl(k_scan_tiles, dim3(grid), dim3(256), 0, as_stream(stream), rows_k, tps_k, counts_c, tile_excl, stream_totals,
-                    S_k, ns_k, seg_k, ticket_k);
-  if (le != cudaSuccess) return fail((int)le, cudaGetErrorString(le));
-  int rc = check_launch("k_scan_tiles");
-  if (rc || fused) return rc;
+  if (tiles_per_stream <= 8 && S <= 0x7fffffff / 32) {
+    // many small streams: a warp per stream, which also delivers the per-stream event totals
+    const bool want = seg && n_slots > 0;
+    int mode = !want ? 0 : (small ? (ticket ? 1 : 0) : (ticket ? 2 : 3));
+    seg_k = mode ? seg : nullptr;
+    ticket_k = ticket;
+    le = launch_pdl(k_scan_small, dim3((unsigned)(((long long)S * 32 + 255) / 256)), dim3(256), 0, as_stream(stream), S_k, tps_k,
+                    ns_k, counts_c, tile_excl, stream_totals, seg_k, ticket_k, mode);
+    if (le != cudaSuccess) return fail((int)le, cudaGetErrorString(le));
+    int rc = check_launch("k_scan_small");
+    if (rc || mode == 1) return rc;
+    if (mode >= 2) {
+      const unsigned blocks = (unsigned)((S + 127) / 128);
+      if (mode == 3) k_seg_scan_streams<<<1, 1024, 0, as_stream(stream)>>>(S, 2 * n_slots, seg);
+      k_seg_fill<<<blocks, 128, 0, as_stream(stream)>>>(S, n_slots, stream_totals, seg);
+      return check_launch("k_seg_fill");
+    }
+    // mode 0 with row pointers wanted (few segments, no ticket): the separate launch below
+  } else {
+    if (tiles_per_stream > 256 && n_rows <= 0x7fffffffll / 256)
+      le = launch_pdl(k_scan_tiles_wide, dim3((unsigned)n_rows), dim3(256), 0, as_stream(stream), tps_k, counts_c, tile_excl,
+                      stream_totals, S_k, ns_k, seg_k, ticket_k);
+    else
+      le = launch_pdl(k_scan_tiles, dim3(grid), dim3(256), 0, as_stream(stream), rows_k, tps_k, counts_c, tile_excl, stream_totals,
+                      S_k, ns_k, seg_k, ticket_k);
+    if (le != cudaSuccess) return fail((int)le, cudaGetErrorString(le));
+    int rc = check_launch("k_scan_tiles");
+    if (rc || fused) return rc;
+  }
+  int rc = DVS_OK;
   if (seg_offsets) {
     if (n_slots == 0) {
       cudaError_t e = cudaMemsetAsync(seg_offsets, 0, sizeof(int64_t), as_stream(stream));
@@ -1199,11 +1274,14 @@ int dvs_aer_expand(int32_t S, int32_t tiles_per_stream, int32_t tile_px, const d
   int tpw = 32;
   while (tpw > 1 && (long long)S * ((2 * tiles_per_stream + tpw - 1) / tpw) < 16384) tpw >>= 1;
   A.tpw = tpw;
-  const int tasks_per_block = 8 * tpw;
+  // streams of one or two tiles (thousands of MNIST-sized streams) have fewer than eight warps' worth of tasks: smaller CTAs
+  // instead of idle warps that hold residency slots
+  const int warps = std::min(8, (2 * tiles_per_stream + tpw - 1) / tpw);
+  const int tasks_per_block = warps * tpw;
   const dim3 grid((unsigned)((2 * tiles_per_stream + tasks_per_block - 1) / tasks_per_block), (unsigned)S);
   const bool ns8 = (A.enc.mode == DVS_ENC_RATE || A.enc.mode == DVS_ENC_TIME) && A.enc.n_slots <= 8;
-  const cudaError_t le = ns8 ? launch_pdl(k_expand<true>, grid, dim3(256), 0, as_stream(stream), A)
-                             : launch_pdl(k_expand<false>, grid, dim3(256), 0, as_stream(stream), A);
+  const cudaError_t le = ns8 ? launch_pdl(k_expand<true>, grid, dim3(32 * warps), 0, as_stream(stream), A)
+                             : launch_pdl(k_expand<false>, grid, dim3(32 * warps), 0, as_stream(stream), A);
   if (le != cudaSuccess) return fail((int)le, cudaGetErrorString(le));
   return check_launch("k_expand");
 }

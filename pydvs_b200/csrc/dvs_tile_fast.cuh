@@ -75,6 +75,13 @@ DEV uint32_t bytes_of_flags4(uint32_t n) { return n * 0x10204080u; }
 #define FAST2_THR_EARLY 1    // adaptive thresholds without inhibition: advanced and stored in the threshold pass itself
 #endif
 constexpr int kFastCap = 2048;  // work-list capacity; denser tiles go to the generic body (redo list)
+// Capacity actually reserved for a launch: a tile cannot hold more candidates than pixels (areas with k x k inhibition),
+// and small tiles (VGA rows, MNIST-sized streams) get many more resident CTAs per SM out of the smaller footprint.
+static inline int fast_cap_of(const TileArgs &A) {
+  const int k2 = A.inh_k >= 2 ? A.inh_k * A.inh_k : 1;
+  const int bound = (A.tile_px + k2 - 1) / k2;
+  return bound >= kFastCap ? kFastCap : (bound + 31) / 32 * 32;
+}
 
 // ---- fast kernel, register-only variant ---------------------------------------------------------
 // Used when no shared-memory plane is needed: inhibition off (PAIR == false: thread owns JH groups in
@@ -135,10 +142,11 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   constexpr bool FUSED2 = FUSED2_SHAPE;
   uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
   uint16_t *wl16 = reinterpret_cast<uint16_t *>(smem_raw);  // ENC != 0: pixel indices only
-  uint2 *rec_sm = reinterpret_cast<uint2 *>(smem_raw + kFastCap * 4);
+  const int cap = STAGED ? kFastCap : A.fast_cap;
+  uint2 *rec_sm = reinterpret_cast<uint2 *>(smem_raw + cap * 4);
   uint32_t *wtot = reinterpret_cast<uint32_t *>(ctl);
   uint16_t *wl_thr = reinterpret_cast<uint16_t *>(wtot + 128 + 2 * (A.enc.mode == DVS_ENC_NONE ? 0 : A.enc.n_slots + 1) + 8);  // ADAPT
-  uint8_t *tr_lut = reinterpret_cast<uint8_t *>(wl_thr + (ADAPT ? kFastCap : 0));  // history_weight != 1: trunc(hw * r), r in [0, 255]
+  uint8_t *tr_lut = reinterpret_cast<uint8_t *>(wl_thr + (ADAPT ? cap : 0));  // history_weight != 1: trunc(hw * r), r in [0, 255]
   const bool decay = !SIMPLE && A.upd.hw_is_one == 0;  // (SIMPLE implies plain rate update, no decay) 0 <= history_weight < 1 (host-checked): every pixel's reference moves
   uint32_t *hist = wtot + 128;
   const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
@@ -423,7 +431,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       A.tile_counts[((size_t)s_idx * A.C + c) * A.tiles_per_stream + t_idx] = 0;
     return;
   }
-  if (unsafe || n_cand > kFastCap) {  // generic body: exact int16 wrap semantics / dense tiles
+  if (unsafe || n_cand > cap) {  // generic body: exact int16 wrap semantics / dense tiles
     if (THR_EARLY) {  // ... which must find the thresholds as they were
 #pragma unroll
       for (int j = 0; j < J; ++j)
@@ -653,7 +661,7 @@ template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT = false>
 __global__ void __launch_bounds__(256, ADAPT ? FAST2_MINB_ADPT : FAST2_MINB) k_tile_fast2(const __grid_constant__ TileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_trigger();
-  fast2_tile<SRC, JH, PAIR, ENC, ADAPT, false>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + kFastCap * 12,
+  fast2_tile<SRC, JH, PAIR, ENC, ADAPT, false>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + A.fast_cap * 12,
                                                   nullptr, nullptr);
 }
 
@@ -662,7 +670,7 @@ template <int SRC, int ENC, bool ADAPT, int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 4 : 2) k_tile_fast4(const __grid_constant__ TileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_trigger();
-  fast2_tile<SRC, 1, true, ENC, ADAPT, false, true>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + kFastCap * 12,
+  fast2_tile<SRC, 1, true, ENC, ADAPT, false, true>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + A.fast_cap * 12,
                                                      nullptr, nullptr);
 }
 
@@ -751,9 +759,10 @@ template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT = false>
 static int launch_fast2(const TileArgs &A_in, int bd, cudaStream_t st) {
   TileArgs A = A_in;
   A.inv_nw = (65536u + (unsigned)(bd / 32) - 1u) / (unsigned)(bd / 32);
+  A.fast_cap = fast_cap_of(A);
   auto k = k_tile_fast2<SRC, JH, PAIR, ENC, ADAPT>;
   const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
-  const size_t smem = kFastCap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t) + (ADAPT ? kFastCap * 2 : 0) + 256;
+  const size_t smem = (size_t)A.fast_cap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t) + (ADAPT ? A.fast_cap * 2 : 0) + 256;
   cudaError_t e;
   if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
     return set_error((int)e, cudaGetErrorString(e));
@@ -798,8 +807,9 @@ template <int SRC, int ENC, bool ADAPT>
 static int launch_fast4(const TileArgs &A_in, cudaStream_t st) {
   TileArgs A = A_in;
   A.inv_nw = (65536u + (unsigned)((A.W / 8 + 31) / 32) - 1u) / (unsigned)((A.W / 8 + 31) / 32);
+  A.fast_cap = fast_cap_of(A);
   const int nh = A.enc.n_slots + 1;
-  const size_t smem = kFastCap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t) + (ADAPT ? kFastCap * 2 : 0) + 256;
+  const size_t smem = (size_t)A.fast_cap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t) + (ADAPT ? A.fast_cap * 2 : 0) + 256;
   cudaError_t e;
   const int gpr = A.W / 8, bd = (gpr + 31) / 32 * 32;
   const dim3 grid((unsigned)A.tiles_per_stream, (unsigned)A.S);

@@ -28,6 +28,7 @@ struct TileArgs {
   int thr_scalar;
   unsigned inv_w;          // ceil(2^32 / W): q / W == umulhi(q, inv_w) for q < 32768
   unsigned inv_nw;         // fast kernels: ceil(2^16 / warps per CTA)
+  int fast_cap;            // fast kernels: work-list capacity of a tile (<= kFastCap; the most candidates a tile can hold)
   int silent_a;            // ranked kernel: abs_diff from which a coded-rate spike falls in no slot (and is not recorded)
   UpdateArgs upd;
   EncArgs enc;

@@ -16,7 +16,7 @@
 //      No ballots, no ranks, no staging in shared memory, no copy-out pass and one barrier less than fast2_tile, which
 //      discovers list membership only inside the per-candidate loop.
 //
-// Shared memory: [wl: kFastCap u32][wtot: 32 u32][hist: 2 * (n_slots + 1) u32]  (~8.5 KB)
+// Shared memory: [wl: fast_cap u32][wtot: 32 u32][hist: 2 * (n_slots + 1) u32]  (~8.5 KB)
 #pragma once
 #include "dvs_tile_fast.cuh"
 
@@ -31,7 +31,7 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
   static_assert(ENC == ENC_RATE_CODED || ENC == ENC_TIME_CODED, "inlined encoders only");
   constexpr int J = 2 * JH;
   uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
-  uint32_t *wtot = wl + kFastCap;
+  uint32_t *wtot = wl + A.fast_cap;
   uint32_t *hist = wtot + 32;
   const int nh = A.enc.n_slots + 1;
 
@@ -257,7 +257,8 @@ static int launch_ranked(const TileArgs &A_in, int bd, cudaStream_t st) {
   // coded rate with drop_silent: spikes with k == 0 (abs_diff // T_enc >= n_slots - 1) are updated but not recorded
   A.silent_a = (ENC == ENC_RATE_CODED && A.drop_silent) ? (A.enc.n_slots - 1) * A.enc.threshold : 0x7fffffff;
   const int nh = A.enc.n_slots + 1;
-  const size_t smem = kFastCap * 4 + (32 + 2 * nh + 4) * sizeof(uint32_t);
+  A.fast_cap = fast_cap_of(A);
+  const size_t smem = (size_t)A.fast_cap * 4 + (32 + 2 * nh + 4) * sizeof(uint32_t);
   cudaError_t e;
   k_tile_ranked<SRC, JH, ENC><<<dim3((unsigned)A.tiles_per_stream, (unsigned)A.S), bd, smem, st>>>(A);
   if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));

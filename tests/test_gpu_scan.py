@@ -24,7 +24,7 @@ def _expected(counts, S, Cn, tps, n_slots):
 
 @pytest.mark.parametrize("S,tps,n_slots", [(1, 1, 1), (3, 31, 4), (5, 255, 8), (4, 256, 8), (7, 257, 8), (32, 1080, 8),
                                             (2, 2048, 3), (3, 2049, 2), (2, 5000, 1), (300, 270, 8), (700, 3, 8),
-                                            (4096, 1, 16), (513, 300, 8)])
+                                            (4096, 1, 16), (513, 300, 8), (4096, 1, 6), (5, 8, 2), (9000, 2, 1), (33, 7, 40)])
 @pytest.mark.parametrize("with_ticket", [False, True])
 def test_scan_matches_numpy(S, tps, n_slots, with_ticket):
     from pydvs_b200 import _lib

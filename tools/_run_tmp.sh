@@ -1,10 +1,9 @@
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo rc=$? >> gpurun_out/pytest.log; tail -5 gpurun_out/pytest.log
-OUT=gpurun_out/shard4; mkdir -p $OUT
+OUT=gpurun_out/shard6; mkdir -p $OUT
 P="--no-e2e --no-cpu-baseline --no-parity --configs none --steps 40 --warmup 5"
-for L in main nopdl; do
-if [ "$L" = "main" ]; then unset PYDVS_B200_LIB; else export PYDVS_B200_LIB=$PWD/pydvs_b200/libpydvs_b200_$L.so; fi
-python bench.py $P --streams 32 > $OUT/${L}_s32.json 2>$OUT/${L}_s32.err
-python bench.py $P --workload 1080p_time_adaptive --streams 8 --settle 8 > $OUT/${L}_c4s8.json 2>$OUT/${L}_c4s8.err
-python bench.py $P --workload vga_rate_inhibition > $OUT/${L}_vga.json 2>$OUT/${L}_vga.err
-python bench.py $P --workload mnist_time_bin_thr_adaptive --settle 4 > $OUT/${L}_mnist.json 2>$OUT/${L}_mnist.err
-done
+python bench.py $P --workload mnist_time_bin_thr_adaptive --settle 4 > $OUT/main_mnist.json 2>$OUT/main_mnist.err
+python bench.py $P --workload vga_rate_inhibition --streams 2048 > $OUT/main_vga2048.json 2>$OUT/main_vga2048.err
+python bench.py $P --workload davis346_rate > $OUT/main_davis.json 2>$OUT/main_davis.err
+python bench.py $P --streams 64 --ring 8 > $OUT/main_s64.json 2>$OUT/main_s64.err
+Q="--no-e2e --no-cpu-baseline --no-parity --configs none --steps 3 --warmup 3"
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 400 --csv --log-file $OUT/launches_mnist.csv python bench.py $Q --workload mnist_time_bin_thr_adaptive --settle 4 --graph off > $OUT/ncu1.log 2>&1
