@@ -62,8 +62,10 @@ WORKLOADS = {
 SUITE = [
     ("cfg5_4k_dense", dict(workload="4k_full_pipeline_rate", pattern="dense", settle=2)),
     ("cfg5_4k_uint8_frames", dict(workload="4k_full_pipeline_rate", frame_dtype="uint8", reuse_headline_ring=True)),
+    ("cfg5_4k_int16_state", dict(workload="4k_full_pipeline_rate", state_dtype="int16", reuse_headline_ring=True)),  # rounds 1-2 layout
     ("cfg5_4k_ring4_periodic_orbit", dict(workload="4k_full_pipeline_rate", ring=4)),   # round 1's headline workload
     ("cfg4_1080p_time_adaptive_64_streams", dict(workload="1080p_time_adaptive", settle=8)),
+    ("cfg4_1080p_time_adaptive_64_streams_int16_state", dict(workload="1080p_time_adaptive", settle=8, state_dtype="int16")),
     ("cfg4_1080p_time_adaptive_8_streams", dict(workload="1080p_time_adaptive", streams=8, settle=8)),
     ("cfg2_mnist_shape_4096_streams_time_bin_thr_adaptive", dict(workload="mnist_time_bin_thr_adaptive", settle=4)),
     ("cfg3_vga_rate_inhibition", dict(workload="vga_rate_inhibition")),
@@ -82,6 +84,9 @@ def parse_args():
     ap.add_argument("--pattern", default="bar", choices=["bar", "dense"],
                     help="bar: moving bar + noise (sparse events); dense: uniform random pixels")
     ap.add_argument("--frame-dtype", default="int16", choices=["int16", "uint8"])
+    ap.add_argument("--state-dtype", default="auto", choices=["auto", "int16", "uint8"],
+                    help="layout of the resident reference / threshold planes: int16 as the reference's API holds them, or "
+                         "one byte per pixel where that is exact (auto: uint8 whenever DVSStreams accepts it)")
     ap.add_argument("--ring", type=int, default=16,
                     help="distinct frames resident per stream.  The bar travels W/64 px per frame; a 4-frame ring settles on a "
                          "period-4 orbit of the state that emits ~60x fewer events than video does, so the default keeps 16")
@@ -150,7 +155,7 @@ def bench_config(args, wl, world):
     return {"workload": args.workload, "width": wl["W"], "height": wl["H"], "streams_total": S_total,
             "coding": wl["output_type"], "inhibition": wl["inh"], "adaptive_threshold": wl["adaptive"],
             "pattern": args.pattern, "frame_dtype": args.frame_dtype, "ring_frames": args.ring,
-            "settle_steps": args.settle, "ref0": wl["ref0"],
+            "settle_steps": args.settle, "ref0": wl["ref0"], "state_dtype": args.state_dtype,
             "l2": ("inputs larger than L2: every step reads another frame of the ring plus the state planes "
                    "(%.2f GB per GPU per step)" % per_gpu_gb) if per_gpu_gb * args.ring > 0.126 else
                   "working set fits in L2 (launch-bound configuration, not an HBM measurement)"}
@@ -424,7 +429,7 @@ class Case:
     """One timed configuration on this rank: state object + frame ring + step counter."""
 
     def __init__(self, args, wl, S, stream_base, device, pattern, frame_dtype, ring_n, graph, ring=None,
-                 pipeline_depth=1, k1_variant="auto"):
+                 pipeline_depth=1, k1_variant="auto", state_dtype=None):
         import torch
         from pydvs_b200 import DVSConfig, DVSStreams
         self.wl, self.S, self.stream_base, self.device = wl, S, stream_base, device
@@ -438,7 +443,8 @@ class Case:
         g = {"auto": "auto", "on": True, "off": False}[graph]
         self.dvs = DVSStreams(cfg, device=device, event_capacity=1 << 16, pipeline_depth=pipeline_depth,
                               force_generic={"auto": 0, "plain": 0, "staged": 3, "generic": 1}[k1_variant],
-                              split_lists=False, graph=g)   # AER events are the output; split_spikes lists are not requested
+                              split_lists=False, graph=g,   # AER events are the output; split_spikes lists are not requested
+                              state_dtype=state_dtype or getattr(args, "state_dtype", "auto"))
         self.ring = ring if ring is not None else make_ring(wl, S, ring_n, pattern, frame_dtype, device, stream_base)
         self.i = 0
         torch.cuda.synchronize()
@@ -562,7 +568,8 @@ class Case:
             slot_off = off[s * per:(s + 1) * per + 1:2].copy() - off[s * per]
             jobs.append({"stream": self.stream_base + s, "wl": self.wl, "n_frames": self.i,
                          "ring": [f[s].cpu().numpy().astype("int16") for f in self.ring],
-                         "ref": dvs.ref[s].cpu().numpy(), "thr": dvs.thr[s].cpu().numpy() if dvs.thr is not None else None,
+                         "ref": dvs.ref_plane(s).cpu().numpy(),
+                         "thr": dvs.thr_plane(s).cpu().numpy() if dvs.thr_plane(s) is not None else None,
                          "keys": keys, "slot_counts": (slot_off[1:] - slot_off[:-1])})
         return jobs
 
@@ -606,7 +613,14 @@ def load_traffic(key):
 
 
 def bytes_per_px(wl, frame_dtype):
+    """frame read + int16 reference read and write (+ int16 threshold read and write)."""
     return (1 if frame_dtype == "uint8" else 2) + 4 + (4 if wl["adaptive"] else 0)
+
+
+def layout_bytes_per_px(wl, frame_dtype, state_dtype):
+    """The same count for the layout actually resident (one-byte state planes halve the state traffic)."""
+    st = 1 if state_dtype == "uint8" else 2
+    return (1 if frame_dtype == "uint8" else 2) + 2 * st + (2 * st if wl["adaptive"] else 0)
 
 
 def pick_streams(S, name):
@@ -628,7 +642,7 @@ def run_suite_entry(args, name, ov, device, barrier, headline_case, peak):
     if ov.get("reuse_headline_ring") and headline_case is not None and headline_case.S == S:
         dt = torch.uint8 if fdt == "uint8" else torch.int16
         ring = [f.to(dt) for f in headline_case.ring]
-    case = Case(args, wl, S, 0, device, pattern, fdt, ring_n, args.graph, ring=ring)
+    case = Case(args, wl, S, 0, device, pattern, fdt, ring_n, args.graph, ring=ring, state_dtype=ov.get("state_dtype"))
     case.settle(ov.get("settle", args.settle))
     K = max(1, args.config_steps)
     t = case.timed(K, 3, barrier)
@@ -638,7 +652,8 @@ def run_suite_entry(args, name, ov, device, barrier, headline_case, peak):
     bpp = bytes_per_px(wl, fdt)
     k1_bytes = bpp * S * case.P
     l2_resident = (bpp + 2) * S * case.P * len(case.ring) < 100e6
-    tr = load_traffic("%s:%s:%s" % (ov["workload"], pattern, fdt))
+    sdt = case.dvs.state_dtype
+    tr = load_traffic("%s:%s:%s%s" % (ov["workload"], pattern, fdt, ":s8" if sdt == "uint8" else ""))
     entry = {"workload": ov["workload"], "width": wl["W"], "height": wl["H"], "streams": S, "coding": wl["output_type"],
              "inhibition": wl["inh"], "adaptive_threshold": wl["adaptive"], "pattern": pattern, "frame_dtype": fdt,
              "ring_frames": len(case.ring), "steps": K, "ms_per_step": ms, "stream_frames_per_s": S * K / (t["elapsed_ms"] / 1e3),
@@ -647,7 +662,10 @@ def run_suite_entry(args, name, ov, device, barrier, headline_case, peak):
              "step_frac": (k1_bytes + 8 * t["events_last_step"]) / (ms / 1e3) / 1e9 / peak,
              "traffic": (tr["bytes_per_px"] * S * case.P) if tr else None,
              "cuda_graph": bool(case.dvs.use_graph), "launches_per_step": case.launches_per_step(),
-             "events_last_step": t["events_last_step"], "tile_rows": case.dvs.tile_rows}
+             "events_last_step": t["events_last_step"], "tile_rows": case.dvs.tile_rows, "state_dtype": sdt,
+             "layout_bytes_per_px": layout_bytes_per_px(wl, fdt, sdt),
+             # (bytes/px * pixels + 8 * events) / time -- K1 writes one 8-byte record per spike
+             "frac_with_events": (k1_bytes + 8 * t["events_last_step"]) / (k1_ms / 1e3) / 1e9 / peak}
     if l2_resident:
         entry["l2_resident"] = "ring + state fit in the 126 MB L2: launch-bound, `frac` is not an HBM fraction"
     del case
@@ -716,7 +734,7 @@ def run_pipeline_entry(args, device, peak):
                      seed=7, **kw)
     cfg = DVSConfig(width=W, height=H, streams=S, output_type="TIME_BIN_THR", threshold=12, adaptive_threshold=True,
                     history_weight=wl["hw"], max_time_ms=wl["max_time_ms"], num_bins=wl["num_bins"], threshold0=12, ref0=0)
-    dvs = DVSStreams(cfg, device=device, event_capacity=S * H * W * 4, split_lists=False)
+    dvs = DVSStreams(cfg, device=device, event_capacity=S * H * W * 4, split_lists=False, state_dtype=args.state_dtype)
     fs, ds, dm = key_params(W, H)
     frames_host = {0: [], 1234: []}
 
@@ -770,8 +788,8 @@ def run_pipeline_entry(args, device, peak):
                 counts, flat = pipe.step_raw(img)
             got = keys[int(off[s * per]):int(off[(s + 1) * per])]
             res_ok.append({"stream": s, "frames_equal": bool(frames_equal),
-                           "ref_equal": bool(np.array_equal(dvs.ref[s].cpu().numpy(), pipe.ref)),
-                           "thr_equal": bool(np.array_equal(dvs.thr[s].cpu().numpy(), pipe.thr)),
+                           "ref_equal": bool(np.array_equal(dvs.ref_plane(s).cpu().numpy(), pipe.ref)),
+                           "thr_equal": bool(np.array_equal(dvs.thr_plane(s).cpu().numpy(), pipe.thr)),
                            "events_equal": bool(np.array_equal(got, flat[:, 0].astype(np.int16)))})
         entry["parity"] = {"streams": [r["stream"] for r in res_ok], "frames": len(frames_host[0]),
                            "frames_equal": all(r["frames_equal"] for r in res_ok), "ref_equal": all(r["ref_equal"] for r in res_ok),
@@ -840,8 +858,8 @@ def run_ours(args, wl, rank, local_rank, world):
     # state of stream 0 for the single-core CPU baseline (same phase as the timed region)
     cpu_state = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_state = ([f[0].cpu().numpy().astype(np.int16) for f in case.ring], dvs.ref[0].cpu().numpy(),
-                     dvs.thr[0].cpu().numpy() if dvs.thr is not None else None, case.i)
+        cpu_state = ([f[0].cpu().numpy().astype(np.int16) for f in case.ring], dvs.ref_plane(0).cpu().numpy(),
+                     dvs.thr_plane(0).cpu().numpy() if dvs.thr_plane(0) is not None else None, case.i)
 
     # ---- e2e: host frames in pinned memory, H2D + step + D2H of the AER result per step ----------------
     e2e = None
@@ -854,8 +872,9 @@ def run_ours(args, wl, rank, local_rank, world):
             case2 = Case.__new__(Case)
             case2.__dict__.update(case.__dict__)
             case2.frame_dtype = "uint8"
-            case2.dvs = DVSStreams(cfg2, device=device, event_capacity=dvs.event_capacity, split_lists=False, graph=False)
-            case2.dvs.ref.copy_(dvs.ref)   # continue from the same state and position in the ring
+            case2.dvs = DVSStreams(cfg2, device=device, event_capacity=dvs.event_capacity, split_lists=False, graph=False,
+                                   state_dtype=dvs.state_dtype)
+            case2.dvs.set_state(ref=dvs._ref)   # continue from the same state and position in the ring
             case2.ring = [f.to(torch.uint8) for f in case.ring]
             e2e["uint8_host_frames"] = run_e2e(args, case2, world, barrier, allmax, "uint8", pool_pin)
             del case2, pool_pin
@@ -935,7 +954,7 @@ def run_ours(args, wl, rank, local_rank, world):
     bpp = bytes_per_px(wl, args.frame_dtype)
     k1_bytes = bpp * S * P
     achieved = k1_bytes / (k1_ms / 1e3) / 1e9
-    tr = load_traffic("%s:%s:%s" % (args.workload, args.pattern, args.frame_dtype))
+    tr = load_traffic("%s:%s:%s%s" % (args.workload, args.pattern, args.frame_dtype, ":s8" if dvs.state_dtype == "uint8" else ""))
     traffic = tr["bytes_per_px"] * S * P if tr else None
     step_bytes = k1_bytes + 8 * events_last_step
     line = {
@@ -950,13 +969,18 @@ def run_ours(args, wl, rank, local_rank, world):
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "frac_of_8tbs_spec": achieved / 8000.0, "bytes_per_px": bpp, "k1_ms": k1_ms,
+                     "state_dtype": dvs.state_dtype,
+                     "layout_bytes_per_px": layout_bytes_per_px(wl, args.frame_dtype, dvs.state_dtype),
+                     "frac_with_events": (k1_bytes + 8 * events_last_step) / (k1_ms / 1e3) / 1e9 / peak,
                      "scan_expand_ms": rest_ms, "k1_share_of_step": (k1_ms / (k1_ms + rest_ms)) if rest_ms else None,
                      "step_achieved_gbs": step_bytes / (elapsed_ms / K / 1e3) / 1e9,
                      "traffic_gbs": (traffic / (k1_ms / 1e3) / 1e9) if traffic else None,
-                     "note": "achieved counts ALGORITHMIC bytes (frame read + reference read + reference write per pixel); the "
-                             "kernel does not write back pixels whose reference is unchanged, so its DRAM traffic "
-                             "(`traffic`, from the ncu capture under profiles/) is lower and frac can exceed 1 while the "
-                             "DRAM itself runs at traffic_gbs"},
+                     "note": "achieved counts SURVEY 8(d)'s ALGORITHMIC bytes (frame read + int16 reference read + reference write "
+                             "per pixel); the kernel does not write back pixels whose reference is unchanged and, with "
+                             "state_dtype uint8, keeps the reference plane in one byte per pixel (exact: every update clips "
+                             "to [0, 255]), so its DRAM traffic (`traffic`, from the ncu capture under profiles/) is lower "
+                             "and frac can exceed 1 while the DRAM itself runs at traffic_gbs; configs.cfg5_4k_int16_state "
+                             "is the same workload on int16 state planes"},
         "clocks": clocks, "gpu_launches": lps * K,
         "events_allgather": {"streams": int(all_counts.numel()), "total_events_last_step": int(all_counts.sum().item())},
     }

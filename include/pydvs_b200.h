@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DVS_ABI_VERSION 3
+#define DVS_ABI_VERSION 4
 
 /* error codes (>= 1000 so they cannot collide with cudaError_t) */
 #define DVS_OK 0
@@ -67,6 +67,7 @@ enum {
 };
 
 enum { DVS_FRAME_I16 = 0, DVS_FRAME_U8 = 1 };
+enum { DVS_STATE_I16 = 0, DVS_STATE_U8 = 1 };  /* dvs_step_params.state_dtype */
 
 /* One spiking pixel, the element of split_spikes' (rows; cols; vals) lists, gs:716-719. */
 typedef struct dvs_record {
@@ -138,12 +139,16 @@ typedef struct dvs_step_params {
   int32_t record_stride;    /* records reserved per tile region; 0 = tile_rows * W.  With k x k inhibition a tile
                              * holds at most (tile_rows / k) * (W / k) records, so callers may pass that bound
                              * (the same number is the `tile_px` argument of dvs_aer_expand / dvs_gather_split) */
-  int32_t reserved0;
+  int32_t state_dtype;      /* DVS_STATE_*: layout of the resident planes `ref` / `thr`.  DVS_STATE_U8 keeps one byte per
+                             * pixel: every update_reference_* rule ends in clip(.., 0, 255) (gs:251, 297, 378, 425) and
+                             * the coded threshold rule in clip(.., min, max) (gs:297), so for planes that start in
+                             * [0, 255] (and 0 <= min_thr <= max_thr <= 255) the values are the reference's own, and the
+                             * pass moves half the state bytes.  Identical events, records and state values.          */
   double history_weight;
   dvs_enc_params enc;
   const void *curr;         /* [S][H][W] frames, int16 or uint8                               */
-  int16_t *ref;             /* [S][H][W] reference state, updated in place                    */
-  int16_t *thr;             /* [S][H][W] threshold state (adaptive), updated in place         */
+  void *ref;                /* [S][H][W] reference state (int16_t or uint8_t per state_dtype), updated in place */
+  void *thr;                /* [S][H][W] threshold state (adaptive; same layout), updated in place            */
   int16_t *diff_out;        /* optional planes (NULL = skip): what thresholded_difference and */
   int16_t *abs_diff_out;    /*   local_inhibition would have returned for this frame          */
   int16_t *spikes_out;

@@ -18,7 +18,8 @@ POL_UP, POL_DOWN, POL_MERGED, POL_RECTIFIED = 0, 1, 2, 3
 UPD_RATE, UPD_RATE_ADPT, UPD_TIME_BIN_RAW, UPD_TIME_BIN_THR, UPD_NONE = 0, 1, 2, 3, 4
 ENC_RATE, ENC_TIME, ENC_TIME_BIN, ENC_TIME_BIN_THR, ENC_NONE = 0, 1, 2, 3, 4
 FRAME_I16, FRAME_U8 = 0, 1
-ABI_VERSION = 3
+STATE_I16, STATE_U8 = 0, 1
+ABI_VERSION = 4
 PATH_GENERIC, PATH_FAST, PATH_FAST_4X4 = 0, 1, 2
 
 
@@ -43,7 +44,7 @@ class StepParams(C.Structure):
                 ("min_thr", C.c_int32), ("max_thr", C.c_int32), ("thr_down", C.c_int32),
                 ("thr_up", C.c_int32), ("max_time_ms", C.c_int32), ("inh_k", C.c_int32),
                 ("polarity", C.c_int32), ("force_generic", C.c_int32), ("drop_silent", C.c_int32),
-                ("record_stride", C.c_int32), ("reserved0", C.c_int32),
+                ("record_stride", C.c_int32), ("state_dtype", C.c_int32),
                 ("history_weight", C.c_double), ("enc", EncParams),
                 ("curr", C.c_void_p), ("ref", C.c_void_p), ("thr", C.c_void_p),
                 ("diff_out", C.c_void_p), ("abs_diff_out", C.c_void_p), ("spikes_out", C.c_void_p),

@@ -21,7 +21,8 @@ STAMP = LIB + ".sha256"  # next to the library: travels with it to the GPU box
 
 UNITS = ["dvs_b200.cu", "tile_pass_i16.cu", "tile_pass_i16_adpt.cu", "tile_pass_u8.cu",
          "tile_pass_u8_adpt.cu", "tile_pass_planes.cu", "tile_fast_i16.cu", "tile_fast_u8.cu",
-         "tile_fast_i16_adpt.cu", "tile_fast_u8_adpt.cu", "dvs_next_rows.cu"]
+         "tile_fast_i16_adpt.cu", "tile_fast_u8_adpt.cu", "tile_fast_i16_s8.cu", "tile_fast_u8_s8.cu",
+         "tile_fast_i16_adpt_s8.cu", "tile_fast_u8_adpt_s8.cu", "dvs_next_rows.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]
 

@@ -1080,6 +1080,12 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
   // force_generic == 3: the persistent staged kernel whenever the tile shape allows it (opt-in, see dvs_tile_fast.cuh)
   A.use_staged = p->force_generic == 3 ? 2 : 0;
   A.curr = p->curr; A.ref = p->ref; A.thr = p->thr;
+  if (p->state_dtype != DVS_STATE_I16 && p->state_dtype != DVS_STATE_U8) return fail(DVS_ERR_INVALID_ARGUMENT, "state_dtype");
+  A.state_u8 = p->state_dtype == DVS_STATE_U8;
+  if (A.state_u8 && p->adaptive &&
+      (p->uncoded || p->update_mode != DVS_UPD_RATE_ADPT || p->min_thr < 0 || p->max_thr > 255 || p->min_thr > p->max_thr))
+    // (the uncoded rule keeps the unclipped threshold, gsu:286-295, which may leave [0, 255])
+    return fail(DVS_ERR_UNSUPPORTED, "one-byte state needs the coded threshold rule with 0 <= min_thr <= max_thr <= 255");
   A.diff_out = p->diff_out; A.abs_out = p->abs_diff_out; A.spk_out = p->spikes_out;
   A.records = p->records; A.tile_counts = p->tile_counts; A.status = p->status;
   const bool u8 = p->frame_dtype == DVS_FRAME_U8;
@@ -1112,6 +1118,7 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
   g_last_path = DVS_PATH_GENERIC;
   if (fast) {
     g_last_path = quad ? DVS_PATH_FAST_4X4 : DVS_PATH_FAST;
+    if (A.state_u8) return u8 ? launch_tile_fast_u8_s8(A, st) : launch_tile_fast_i16_s8(A, st);
     return u8 ? launch_tile_fast_u8(A, st) : launch_tile_fast_i16(A, st);
   }
   // adaptive fast path: coded rate_adpt rule, no history decay, inhibition off or 2x2 on two-row tiles
@@ -1127,6 +1134,7 @@ int dvs_step_fused(const dvs_step_params *p, void *stream) {
                          !p->diff_out && !p->abs_diff_out && !p->spikes_out && p->force_generic != 1 && p->redo && A.S <= 65535;
   if (fast_adpt) {
     g_last_path = quad ? DVS_PATH_FAST_4X4 : DVS_PATH_FAST;
+    if (A.state_u8) return u8 ? launch_tile_fast_u8_adpt_s8(A, st) : launch_tile_fast_i16_adpt_s8(A, st);
     return u8 ? launch_tile_fast_u8_adpt(A, st) : launch_tile_fast_i16_adpt(A, st);
   }
   if (u8) return p->adaptive ? launch_tile_pass_u8_adpt(A, st) : launch_tile_pass_u8(A, st);

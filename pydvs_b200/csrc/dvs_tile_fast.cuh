@@ -21,6 +21,56 @@ namespace dvs {
 
 DEV uint4 ld16_stream(const void *p) { return __ldcs(reinterpret_cast<const uint4 *>(p)); }
 
+// state planes (reference, thresholds) in either layout: element type, and 8 consecutive pixels <-> four words of two
+// 16-bit lanes (ST_U8: one 8-byte access, bytes widened / narrowed by PRMT; every lane is in [0, 255] on this path)
+template <int ST> struct state_elem { using type = int16_t; };
+template <> struct state_elem<ST_U8> { using type = uint8_t; };
+template <int ST>
+DEV void ld_state8(const void *p, uint32_t (&pk)[4]) {
+  if (ST == ST_U8) {
+    const uint2 v = *reinterpret_cast<const uint2 *>(p);
+    pk[0] = __byte_perm(v.x, 0, 0x4140); pk[1] = __byte_perm(v.x, 0, 0x4342);
+    pk[2] = __byte_perm(v.y, 0, 0x4140); pk[3] = __byte_perm(v.y, 0, 0x4342);
+  } else {
+    const uint4 v = ld16(p);
+    pk[0] = v.x; pk[1] = v.y; pk[2] = v.z; pk[3] = v.w;
+  }
+}
+// The same in two steps, so that a thread can have ALL its loads in flight before the first PRMT waits for one of them
+// (ptxas keeps an unpack that directly follows its load ahead of the next load: the loads would complete one by one):
+// ld8_raw<BYTES> fetches 8 pixels (BYTES = 1: 8 bytes in raw[0..1], BYTES = 2: 16 bytes), widen8<BYTES> turns them
+// into the four words of two 16-bit lanes in place.
+template <int BYTES, bool STREAM>
+DEV void ld8_raw(const void *p, uint32_t (&raw)[4]) {
+  if (BYTES == 1) {
+    const uint2 v = STREAM ? __ldcs(reinterpret_cast<const uint2 *>(p)) : *reinterpret_cast<const uint2 *>(p);
+    raw[0] = v.x; raw[1] = v.y;
+  } else {
+    const uint4 v = STREAM ? ld16_stream(p) : ld16(p);
+    raw[0] = v.x; raw[1] = v.y; raw[2] = v.z; raw[3] = v.w;
+  }
+}
+template <int BYTES>
+DEV void widen8(uint32_t (&pk)[4]) {
+  if (BYTES == 1) {
+    const uint32_t x = pk[0], y = pk[1];
+    pk[0] = __byte_perm(x, 0, 0x4140); pk[1] = __byte_perm(x, 0, 0x4342);
+    pk[2] = __byte_perm(y, 0, 0x4140); pk[3] = __byte_perm(y, 0, 0x4342);
+  }
+}
+template <int ST>
+DEV void st_state8(void *p, const uint32_t (&pk)[4]) {
+  if (ST == ST_U8)
+    *reinterpret_cast<uint2 *>(p) = make_uint2(__byte_perm(pk[0], pk[1], 0x6420), __byte_perm(pk[2], pk[3], 0x6420));
+  else st16(p, pk);
+}
+// one state pixel as an unsigned value (the int16 layout is read as uint16: in [0, 255] wherever this is used)
+template <int ST>
+DEV int state_px(const void *plane, int q) {
+  if (ST == ST_U8) return (int)static_cast<const uint8_t *>(plane)[q];
+  return (int)static_cast<const uint16_t *>(plane)[q];
+}
+
 // PRMT with the full selector (bit 3 of a selector nibble replicates the sign bit of the chosen byte over the target
 // byte; __byte_perm() ignores that bit, hence the inline PTX)
 template <uint32_t SEL>
@@ -113,10 +163,12 @@ DEV int adpt_div(int a, int thr) {
 // two complete 4x4 areas (columns 0-3 and 4-7 of its block) in registers, the arg-max is a packed maximum over keys
 // abs_diff * 16 + (15 - index in the area), and the winners go to the index-only work list (ENC != 0).  Rows of up to
 // 4096 pixels: CTAs of up to 512 threads.
-template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT, bool STAGED, bool QUAD = false>
+template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT, bool STAGED, bool QUAD = false, int ST = ST_I16>
 DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigned char *smem_raw, unsigned char *ctl,
                     const unsigned char *st_cur, const unsigned char *st_ref) {
   static_assert(!QUAD || (PAIR && JH == 1 && ENC != ENC_ANY && !STAGED), "4x4 variant: one column block, inlined encoders");
+  static_assert(!STAGED || ST == ST_I16, "the staged rows are int16");
+  using state_t = typename state_elem<ST>::type;
   constexpr int J = QUAD ? 4 : (PAIR ? 2 * JH : JH);
   constexpr bool SIMPLE = ENC != ENC_ANY;
   // index-only work list (see above), K1 ms at 64 streams with / without it (gpurun sweep, round 2): uint8 4K frames
@@ -156,7 +208,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   const int row0 = t_idx * A.tile_rows;
   const int npx = min(A.tile_rows, A.H - row0) * A.W;  // multiple of 8 (host-checked)
   const size_t plane_off = ((size_t)s_idx * A.H + row0) * A.W;
-  int16_t *const ref_t = A.ref + plane_off;
+  state_t *const ref_t = static_cast<state_t *>(A.ref) + plane_off;
   const unsigned char *const cur_t = static_cast<const unsigned char *>(A.curr) + plane_off * (SRC == SRC_U8 ? 1 : 2);
   const int gpr = A.W >> 3;  // groups of 8 pixels per row
 
@@ -175,32 +227,32 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     return (j * (int)blockDim.x + tid) * 8;
   };
   const unsigned char *const cur_thread = cur_t + (size_t)tid * 8 * (SRC == SRC_U8 ? 1 : 2);
-  int16_t *const ref_thread = ref_t + tid * 8;
+  state_t *const ref_thread = ref_t + tid * 8;
 
   // ---- 1. loads: all 2 * J 128-bit requests of the thread are in flight before first use --------
   uint32_t c_pk[J][4], r_pk[J][4], t_pk[ADAPT ? J : 1][4];
   bool have[J];
-  int16_t *const thr_t = ADAPT ? A.thr + plane_off : nullptr;
+  state_t *const thr_t = ADAPT ? static_cast<state_t *>(A.thr) + plane_off : nullptr;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int q0 = PAIR ? off_of(j) + tid * 8 : q0_of(j), off = off_of(j);
     have[j] = PAIR ? in_tile(j) : q0 < npx;
     if (have[j]) {
-      if (ADAPT) {
-        const uint4 t = ld16(thr_t + q0);
-        t_pk[j][0] = t.x; t_pk[j][1] = t.y; t_pk[j][2] = t.z; t_pk[j][3] = t.w;
-      }
-      if (SRC == SRC_U8) {
-        const uint2 v = STAGED ? *reinterpret_cast<const uint2 *>(st_cur + q0) : __ldcs(reinterpret_cast<const uint2 *>(PAIR ? cur_thread + off : cur_t + q0));
-        c_pk[j][0] = __byte_perm(v.x, 0, 0x4140); c_pk[j][1] = __byte_perm(v.x, 0, 0x4342);
-        c_pk[j][2] = __byte_perm(v.y, 0, 0x4140); c_pk[j][3] = __byte_perm(v.y, 0, 0x4342);
-      } else {
-        const uint4 v = STAGED ? *reinterpret_cast<const uint4 *>(st_cur + 2 * q0) : ld16_stream(PAIR ? cur_thread + 2 * off : cur_t + 2 * q0);
-        c_pk[j][0] = v.x; c_pk[j][1] = v.y; c_pk[j][2] = v.z; c_pk[j][3] = v.w;
-      }
-      const uint4 r = STAGED ? *reinterpret_cast<const uint4 *>(st_ref + 2 * q0) : ld16(PAIR ? ref_thread + off : ref_t + q0);
-      r_pk[j][0] = r.x; r_pk[j][1] = r.y; r_pk[j][2] = r.z; r_pk[j][3] = r.w;
+      constexpr int CB = SRC == SRC_U8 ? 1 : 2, SB = ST == ST_U8 ? 1 : 2;
+      if (ADAPT) ld8_raw<SB, false>(thr_t + q0, t_pk[j]);
+      if (STAGED) ld8_raw<CB, false>(st_cur + CB * q0, c_pk[j]);
+      else ld8_raw<CB, true>(PAIR ? cur_thread + CB * off : cur_t + CB * q0, c_pk[j]);
+      if (STAGED) ld8_raw<2, false>(st_ref + 2 * q0, r_pk[j]);
+      else ld8_raw<SB, false>(PAIR ? ref_thread + off : ref_t + q0, r_pk[j]);
     }
+  }
+  // bytes -> 16-bit lanes only after every load has been issued (see ld8_raw)
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    if (!have[j]) continue;
+    if (ADAPT) widen8<(ST == ST_U8 ? 1 : 2)>(t_pk[ADAPT ? j : 0]);
+    widen8<(SRC == SRC_U8 ? 1 : 2)>(c_pk[j]);
+    if (!STAGED) widen8<(ST == ST_U8 ? 1 : 2)>(r_pk[j]);
   }
   if (tid < 2 * nh) hist[tid] = 0;
   for (int i = blockDim.x + tid; i < 2 * nh; i += blockDim.x) hist[i] = 0;
@@ -247,7 +299,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
 #pragma unroll
       for (int w = 0; w < 4; ++w) wle[h][w] = 0u;
       if (!have[ju]) continue;
-      rng |= ((r_pk[ju][0] | r_pk[ju][1] | r_pk[ju][2]) | r_pk[ju][3]) | ((r_pk[jl][0] | r_pk[jl][1] | r_pk[jl][2]) | r_pk[jl][3]);
+      if (ST != ST_U8) rng |= ((r_pk[ju][0] | r_pk[ju][1] | r_pk[ju][2]) | r_pk[ju][3]) | ((r_pk[jl][0] | r_pk[jl][1] | r_pk[jl][2]) | r_pk[jl][3]);
       rng |= ((c_pk[ju][0] | c_pk[ju][1] | c_pk[ju][2]) | c_pk[ju][3]) | ((c_pk[jl][0] | c_pk[jl][1] | c_pk[jl][2]) | c_pk[jl][3]);
       const int qu = q0_of(ju);
       uint32_t ku = 0, kl = 0;
@@ -286,14 +338,14 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       else fl[w] = (a + kadd) & 0x80008000u;                 // spike flags at bits 15 / 31
     }
     if (ADAPT) tmax = __vmaxu2(tmax, __vmaxu2(__vmaxu2(t_pk[j][0], t_pk[j][1]), __vmaxu2(t_pk[j][2], t_pk[j][3])));
-    rng |= (r_pk[j][0] | r_pk[j][1] | r_pk[j][2]) | r_pk[j][3];
+    if (ST != ST_U8) rng |= (r_pk[j][0] | r_pk[j][1] | r_pk[j][2]) | r_pk[j][3];  // one-byte state cannot leave [0, 255]
     if (SRC != SRC_U8) rng |= (c_pk[j][0] | c_pk[j][1] | c_pk[j][2]) | c_pk[j][3];
     if (fl[0] | fl[1] | fl[2] | fl[3]) flags8[j] = flags4_of(fl[0], fl[1]) | (flags4_of(fl[2], fl[3]) << 4);
     if (THR_EARLY) {
       uint32_t tn[4];
 #pragma unroll
       for (int w = 0; w < 4; ++w) tn[w] = thr_new(t_pk[ADAPT ? j : 0][w], msb_lane_mask(fl[w]));
-      st16(thr_t + q0_of(j), tn);
+      st_state8<ST>(thr_t + q0_of(j), tn);
     }
   }
   }
@@ -379,7 +431,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       tn[1] = thr_new(t_pk[ADAPT ? j : 0][1], prmt<0xBBAAu>(g01));
       tn[2] = thr_new(t_pk[ADAPT ? j : 0][2], prmt<0x9988u>(g23));
       tn[3] = thr_new(t_pk[ADAPT ? j : 0][3], prmt<0xBBAAu>(g23));
-      st16(thr_t + q0_of(j), tn);
+      st_state8<ST>(thr_t + q0_of(j), tn);
     }
   };
   // history_weight != 1: the reference of every pixel decays (clip(trunc(hw * r) + 0, 0, 255)); candidates are
@@ -392,7 +444,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
 #pragma unroll
       for (int w = 0; w < 4; ++w)
         rn[w] = (uint32_t)tr_lut[r_pk[j][w] & 0xff] | ((uint32_t)tr_lut[(r_pk[j][w] >> 16) & 0xff] << 16);
-      st16(ref_t + q0_of(j), rn);
+      st_state8<ST>(ref_t + q0_of(j), rn);
     }
   };
 #pragma unroll
@@ -435,7 +487,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     if (THR_EARLY) {  // ... which must find the thresholds as they were
 #pragma unroll
       for (int j = 0; j < J; ++j)
-        if (have[j]) st16(thr_t + q0_of(j), t_pk[ADAPT ? j : 0]);
+        if (have[j]) st_state8<ST>(thr_t + q0_of(j), t_pk[ADAPT ? j : 0]);
     }
     if (tid == 0) A.redo[2 + atomicAdd(A.redo, 1)] = tile;
     return;
@@ -570,10 +622,10 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       if (QONLY) {  // index-only entry: fetch the pixel again (both values are in [0, 255]: the tile passed the range vote)
         q = wl16[i];
         // the tile's frame pointer is rebuilt from the reference pointer (kernel parameters are free, live registers are not)
-        const long long boff = reinterpret_cast<const char *>(ref_t) - reinterpret_cast<const char *>(A.ref);
-        const unsigned char *cur_q = static_cast<const unsigned char *>(A.curr) + (SRC == SRC_U8 ? (boff >> 1) + q : boff + 2 * q);
+        const long long poff = (ref_t - static_cast<const state_t *>(A.ref)) + q;  // pixel index in the planes
+        const unsigned char *cur_q = static_cast<const unsigned char *>(A.curr) + (SRC == SRC_U8 ? poff : 2 * poff);
         const int c = SRC == SRC_U8 ? (int)__ldg(cur_q) : (int)__ldg(reinterpret_cast<const uint16_t *>(cur_q));
-        r = (int)reinterpret_cast<const uint16_t *>(ref_t)[q];
+        r = state_px<ST>(ref_t, q);
         neg = c < r;
         a = neg ? r - c : c - r;
       } else {
@@ -586,7 +638,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       else { y = (int)__umulhi((unsigned)q, A.inv_w); x = q - y * A.W; }
       int upd;
       if (ADAPT) {  // gs:287-289: (a // thr) [* min_threshold below]
-        const int th_old = TLATE ? (int)reinterpret_cast<const uint16_t *>(thr_t)[q] : (int)wl_thr[i];
+        const int th_old = TLATE ? state_px<ST>(thr_t, q) : (int)wl_thr[i];
         upd = SIMPLE ? adpt_div(a, th_old) : np_floordiv(a, th_old);
       }
       else if (SIMPLE || A.upd.mode == DVS_UPD_RATE) upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;  // gs:244-249
@@ -598,8 +650,8 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       }
       if (ADAPT) {  // gs:289: int16 products and sums wrap before the clip (thresholds below min_threshold can get there)
         const int u = w16((neg ? -upd : upd) * A.upd.min_thr);
-        ref_t[q] = (int16_t)clip(w16(r + u), 0, 255);
-      } else ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
+        ref_t[q] = (state_t)clip(w16(r + u), 0, 255);
+      } else ref_t[q] = (state_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
       int desc = 0;
       if (ENC == ENC_RATE_CODED) {
         tp = !neg; tn = neg;
@@ -657,20 +709,20 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
 #ifndef FAST2_MINB_ADPT
 #define FAST2_MINB_ADPT 4
 #endif
-template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT = false>
+template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT = false, int ST = ST_I16>
 __global__ void __launch_bounds__(256, ADAPT ? FAST2_MINB_ADPT : FAST2_MINB) k_tile_fast2(const __grid_constant__ TileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_trigger();
-  fast2_tile<SRC, JH, PAIR, ENC, ADAPT, false>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + A.fast_cap * 12,
+  fast2_tile<SRC, JH, PAIR, ENC, ADAPT, false, false, ST>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + A.fast_cap * 12,
                                                   nullptr, nullptr);
 }
 
 // 4x4 inhibition: one column block per thread over four rows; MAXT = 256 (rows up to 2048 px) or 512 (up to 4096 px)
-template <int SRC, int ENC, bool ADAPT, int MAXT>
+template <int SRC, int ENC, bool ADAPT, int MAXT, int ST = ST_I16>
 __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 4 : 2) k_tile_fast4(const __grid_constant__ TileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_trigger();
-  fast2_tile<SRC, 1, true, ENC, ADAPT, false, true>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + A.fast_cap * 12,
+  fast2_tile<SRC, 1, true, ENC, ADAPT, false, true, ST>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + A.fast_cap * 12,
                                                      nullptr, nullptr);
 }
 
@@ -729,7 +781,7 @@ __global__ void __launch_bounds__(256, FAST2S_MINB) k_tile_fast2s(const __grid_c
     unsigned char *dst = smem_raw + (size_t)stage * stage_bytes;
     mbar_expect_tx(&bars[stage], (uint32_t)(npx * (elem + 2)));
     bulk_g2s(dst, static_cast<const unsigned char *>(A.curr) + plane_off * elem, (uint32_t)(npx * elem), &bars[stage]);
-    bulk_g2s(dst + cur_bytes_max, reinterpret_cast<const unsigned char *>(A.ref + plane_off), (uint32_t)(npx * 2), &bars[stage]);
+    bulk_g2s(dst + cur_bytes_max, reinterpret_cast<const unsigned char *>(static_cast<const int16_t *>(A.ref) + plane_off), (uint32_t)(npx * 2), &bars[stage]);
   };
 
   if (threadIdx.x == 0) {
@@ -755,12 +807,12 @@ __global__ void __launch_bounds__(256, FAST2S_MINB) k_tile_fast2s(const __grid_c
   }
 }
 
-template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT = false>
+template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT = false, int ST = ST_I16>
 static int launch_fast2(const TileArgs &A_in, int bd, cudaStream_t st) {
   TileArgs A = A_in;
   A.inv_nw = (65536u + (unsigned)(bd / 32) - 1u) / (unsigned)(bd / 32);
   A.fast_cap = fast_cap_of(A);
-  auto k = k_tile_fast2<SRC, JH, PAIR, ENC, ADAPT>;
+  auto k = k_tile_fast2<SRC, JH, PAIR, ENC, ADAPT, ST>;
   const int nh = A.enc.mode == DVS_ENC_NONE ? 0 : (A.enc.n_slots + 1);
   const size_t smem = (size_t)A.fast_cap * 12 + (128 + 2 * nh + 8) * sizeof(uint32_t) + (ADAPT ? A.fast_cap * 2 : 0) + 256;
   cudaError_t e;
@@ -768,7 +820,7 @@ static int launch_fast2(const TileArgs &A_in, int bd, cudaStream_t st) {
     return set_error((int)e, cudaGetErrorString(e));
   const long long tiles = (long long)A.S * A.tiles_per_stream;
   bool staged = false;
-  if constexpr (!ADAPT && PAIR && ENC != ENC_TIME_CODED) {
+  if constexpr (!ADAPT && PAIR && ENC != ENC_TIME_CODED && ST == ST_I16) {
     // persistent staged kernel: worth it once every resident CTA has several tiles to walk
     const int stage_bytes = (A.tile_px * ((SRC == SRC_U8 ? 1 : 2) + 2) + 127) & ~127;
     const size_t smem_s = 2 * (size_t)stage_bytes + (((128 + 2 * nh + 8) * 4 + 256 + 15) & ~15) + 16;
@@ -803,7 +855,7 @@ static int launch_fast2(const TileArgs &A_in, int bd, cudaStream_t st) {
   return DVS_OK;
 }
 
-template <int SRC, int ENC, bool ADAPT>
+template <int SRC, int ENC, bool ADAPT, int ST = ST_I16>
 static int launch_fast4(const TileArgs &A_in, cudaStream_t st) {
   TileArgs A = A_in;
   A.inv_nw = (65536u + (unsigned)((A.W / 8 + 31) / 32) - 1u) / (unsigned)((A.W / 8 + 31) / 32);
@@ -814,12 +866,12 @@ static int launch_fast4(const TileArgs &A_in, cudaStream_t st) {
   const int gpr = A.W / 8, bd = (gpr + 31) / 32 * 32;
   const dim3 grid((unsigned)A.tiles_per_stream, (unsigned)A.S);
   if (bd <= 256) {
-    auto k = k_tile_fast4<SRC, ENC, ADAPT, 256>;
+    auto k = k_tile_fast4<SRC, ENC, ADAPT, 256, ST>;
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
       return set_error((int)e, cudaGetErrorString(e));
     k<<<grid, bd, smem, st>>>(A);
   } else {
-    auto k = k_tile_fast4<SRC, ENC, ADAPT, 512>;
+    auto k = k_tile_fast4<SRC, ENC, ADAPT, 512, ST>;
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
       return set_error((int)e, cudaGetErrorString(e));
     k<<<grid, bd, smem, st>>>(A);
@@ -841,13 +893,13 @@ static int launch_fast4(const TileArgs &A_in, cudaStream_t st) {
 #ifndef FAST2_RANKED
 #define FAST2_RANKED 1
 #endif
-template <int SRC, int JH, int ENC>
+template <int SRC, int JH, int ENC, int ST>
 static int launch_ranked(const TileArgs &A_in, int bd, cudaStream_t st);
 
 // Caller guarantees: vec_ok (incl. the threshold plane when ADAPT), W % 8 == 0, <= 1024 groups per tile, inhibition
 // off or 2x2 on two-row tiles; static: 2 <= T, rate or time-binary update, history_weight in [0, 1], max_time_ms >= 0;
 // adaptive: rate_adpt update, history_weight in [0, 1], 0 <= min <= max <= 32767, 0 <= up, down <= 32767; no debug planes.
-template <int SRC, bool ADAPT>
+template <int SRC, bool ADAPT, int ST = ST_I16>
 static int dispatch_fast_shapes(const TileArgs &A, cudaStream_t st) {
   const int items = A.tile_px / 8;
   // inlined membership / slot / histogram and index-only work list: MERGED lists of the coded module, coded RATE
@@ -860,14 +912,14 @@ static int dispatch_fast_shapes(const TileArgs &A, cudaStream_t st) {
   else if (coded && A.enc.mode == DVS_ENC_TIME && A.enc.n_slots >= 1) enc = ENC_TIME_CODED;
   auto round32 = [](int x) { return (x + 31) / 32 * 32; };
   if (A.inh_k == 4) {  // caller: four-row tiles, W <= 4096, enc != ENC_ANY (dvs_step_fused checks fast4_ok())
-    if (enc == ENC_RATE_CODED) return launch_fast4<SRC, ENC_RATE_CODED, ADAPT>(A, st);
-    if (enc == ENC_TIME_CODED) return launch_fast4<SRC, ENC_TIME_CODED, ADAPT>(A, st);
+    if (enc == ENC_RATE_CODED) return launch_fast4<SRC, ENC_RATE_CODED, ADAPT, ST>(A, st);
+    if (enc == ENC_TIME_CODED) return launch_fast4<SRC, ENC_TIME_CODED, ADAPT, ST>(A, st);
     return set_error(DVS_ERR_UNSUPPORTED, "internal: 4x4 fast path needs an inlined encoder");
   }
 #define DVS_LAUNCH_ENC(JH_, PAIR_, BD_)                                                                      \
-  (enc == ENC_RATE_CODED   ? launch_fast2<SRC, JH_, PAIR_, ENC_RATE_CODED, ADAPT>(A, BD_, st)                 \
-   : enc == ENC_TIME_CODED ? launch_fast2<SRC, JH_, PAIR_, ENC_TIME_CODED, ADAPT>(A, BD_, st)                 \
-                           : launch_fast2<SRC, JH_, PAIR_, ENC_ANY, ADAPT>(A, BD_, st))
+  (enc == ENC_RATE_CODED   ? launch_fast2<SRC, JH_, PAIR_, ENC_RATE_CODED, ADAPT, ST>(A, BD_, st)             \
+   : enc == ENC_TIME_CODED ? launch_fast2<SRC, JH_, PAIR_, ENC_TIME_CODED, ADAPT, ST>(A, BD_, st)             \
+                           : launch_fast2<SRC, JH_, PAIR_, ENC_ANY, ADAPT, ST>(A, BD_, st))
   if (A.inh_k != 2) {
     if (items <= 256) return DVS_LAUNCH_ENC(1, false, round32(items));
 #if FAST2_J2
@@ -879,10 +931,10 @@ static int dispatch_fast_shapes(const TileArgs &A, cudaStream_t st) {
   if constexpr (FAST2_RANKED && !ADAPT) {
     if (enc != ENC_ANY && A.use_staged == 0) {
       if (gpr <= 256)
-        return enc == ENC_RATE_CODED ? launch_ranked<SRC, 1, ENC_RATE_CODED>(A, round32(gpr), st)
-                                     : launch_ranked<SRC, 1, ENC_TIME_CODED>(A, round32(gpr), st);
-      return enc == ENC_RATE_CODED ? launch_ranked<SRC, 2, ENC_RATE_CODED>(A, round32((gpr + 1) / 2), st)
-                                   : launch_ranked<SRC, 2, ENC_TIME_CODED>(A, round32((gpr + 1) / 2), st);
+        return enc == ENC_RATE_CODED ? launch_ranked<SRC, 1, ENC_RATE_CODED, ST>(A, round32(gpr), st)
+                                     : launch_ranked<SRC, 1, ENC_TIME_CODED, ST>(A, round32(gpr), st);
+      return enc == ENC_RATE_CODED ? launch_ranked<SRC, 2, ENC_RATE_CODED, ST>(A, round32((gpr + 1) / 2), st)
+                                   : launch_ranked<SRC, 2, ENC_TIME_CODED, ST>(A, round32((gpr + 1) / 2), st);
     }
   }
   if (gpr <= 256) return DVS_LAUNCH_ENC(1, true, round32(gpr));
@@ -890,10 +942,10 @@ static int dispatch_fast_shapes(const TileArgs &A, cudaStream_t st) {
 #undef DVS_LAUNCH_ENC
 }
 
-template <int SRC>
-static int dispatch_fast(const TileArgs &A, cudaStream_t st) { return dispatch_fast_shapes<SRC, false>(A, st); }
+template <int SRC, int ST = ST_I16>
+static int dispatch_fast(const TileArgs &A, cudaStream_t st) { return dispatch_fast_shapes<SRC, false, ST>(A, st); }
 
-template <int SRC>
-static int dispatch_fast_adpt(const TileArgs &A, cudaStream_t st) { return dispatch_fast_shapes<SRC, true>(A, st); }
+template <int SRC, int ST = ST_I16>
+static int dispatch_fast_adpt(const TileArgs &A, cudaStream_t st) { return dispatch_fast_shapes<SRC, true, ST>(A, st); }
 
 }  // namespace dvs

@@ -20,12 +20,17 @@ namespace dvs {
 // ================================================================================================
 enum { SRC_I16 = 0, SRC_U8 = 1, SRC_PLANES = 2 };
 enum { INH_NONE = 0, INH_K2 = 2, INH_GENERIC = -1 };
+// layout of the resident state planes (reference, thresholds): int16 as the reference's API holds them, or one byte per
+// pixel (dvs_step_params.state_dtype == DVS_STATE_U8: every update rule clips the reference to [0, 255] and the coded
+// threshold rule to [min, max], so with 0 <= min <= max <= 255 nothing is lost and the pass moves half the state bytes)
+enum { ST_I16 = 0, ST_U8 = 1 };
 
 struct TileArgs {
   int S, H, W, tile_rows, tiles_per_stream, tile_px, C;
   int rec_stride;          // records reserved per tile region (tile_px, or the inhibition bound tile_px / k^2)
   int adaptive, polarity, uncoded, inh_k, vec_ok, fast_hist, drop_silent, use_staged;
   int thr_scalar;
+  int state_u8;            // ref / thr planes hold one byte per pixel (ST_U8)
   unsigned inv_w;          // ceil(2^32 / W): q / W == umulhi(q, inv_w) for q < 32768
   unsigned inv_nw;         // fast kernels: ceil(2^16 / warps per CTA)
   int fast_cap;            // fast kernels: work-list capacity of a tile (<= kFastCap; the most candidates a tile can hold)
@@ -34,7 +39,7 @@ struct TileArgs {
   EncArgs enc;
   const void *curr;        // frames (SRC_I16 / SRC_U8) or spikes plane (SRC_PLANES)
   const int16_t *abs_in;   // SRC_PLANES
-  int16_t *ref, *thr;
+  void *ref, *thr;         // state planes, int16 or uint8 (state_u8)
   int16_t *diff_out, *abs_out, *spk_out;
   dvs_record *records;
   uint32_t *tile_counts;
@@ -79,6 +84,25 @@ DEV void store8_i16(int16_t *base, size_t off, int nvalid, bool vec, const uint3
     for (int p = 0; p < 8; ++p)
       if (p < nvalid) base[off + p] = (int16_t)get16(pk, p);
   }
+}
+
+DEV void store8_u8(uint8_t *base, size_t off, int nvalid, bool vec, const uint32_t (&pk)[4]) {
+  if (vec && nvalid == 8)
+    *reinterpret_cast<uint2 *>(base + off) = make_uint2(__byte_perm(pk[0], pk[1], 0x6420), __byte_perm(pk[2], pk[3], 0x6420));
+  else {
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+      if (p < nvalid) base[off + p] = (uint8_t)get16(pk, p);
+  }
+}
+// state planes in either layout (generic body: a uniform run-time branch; the fast kernels are templated on ST_*)
+DEV void load8_state(const void *base, bool u8, size_t off, int nvalid, bool vec, uint32_t (&pk)[4]) {
+  if (u8) load8_u8(static_cast<const uint8_t *>(base), off, nvalid, vec, pk);
+  else load8_i16(static_cast<const int16_t *>(base), off, nvalid, vec, pk);
+}
+DEV void store8_state(void *base, bool u8, size_t off, int nvalid, bool vec, const uint32_t (&pk)[4]) {
+  if (u8) store8_u8(static_cast<uint8_t *>(base), off, nvalid, vec, pk);
+  else store8_i16(static_cast<int16_t *>(base), off, nvalid, vec, pk);
 }
 
 // sign codes, 2 bits per pixel: 0 -> 0, 1 -> +1, 2 -> -1
@@ -291,8 +315,8 @@ DEV void tile_body(const TileArgs &A, const int tile) {
       else if (SRC == SRC_U8) load8_u8(static_cast<const uint8_t *>(A.curr), plane_off + q0, nval[j], vec, c_pk[j]);
       else load8_i16(static_cast<const int16_t *>(A.curr), plane_off + q0, nval[j], vec, c_pk[j]);
       if (SRC == SRC_PLANES) load8_i16(A.abs_in, plane_off + q0, nval[j], vec, a_pk[j]);
-      else load8_i16(A.ref, plane_off + q0, nval[j], vec, r_pk[j]);
-      if (ADAPT) load8_i16(A.thr, plane_off + q0, nval[j], vec, t_pk[j]);
+      else load8_state(A.ref, A.state_u8 != 0, plane_off + q0, nval[j], vec, r_pk[j]);
+      if (ADAPT) load8_state(A.thr, A.state_u8 != 0, plane_off + q0, nval[j], vec, t_pk[j]);
     }
   }
 #pragma unroll
@@ -412,8 +436,8 @@ DEV void tile_body(const TileArgs &A, const int tile) {
       }
     }
     if (SRC != SRC_PLANES) {
-      if (A.upd.mode != DVS_UPD_NONE) store8_i16(A.ref, plane_off + q0, nval[j], vec, rn_pk);
-      if (ADAPT && A.upd.mode == DVS_UPD_RATE_ADPT) store8_i16(A.thr, plane_off + q0, nval[j], vec, tn_pk);
+      if (A.upd.mode != DVS_UPD_NONE) store8_state(A.ref, A.state_u8 != 0, plane_off + q0, nval[j], vec, rn_pk);
+      if (ADAPT && A.upd.mode == DVS_UPD_RATE_ADPT) store8_state(A.thr, A.state_u8 != 0, plane_off + q0, nval[j], vec, tn_pk);
       if (A.spk_out) store8_i16(A.spk_out, plane_off + q0, nval[j], vec, s_pk);
     }
   }
@@ -530,5 +554,10 @@ int launch_tile_fast_u8(const TileArgs &A, cudaStream_t st);
 // fast path with a per-pixel adaptive threshold plane (coded update_reference_rate_adpt, history_weight == 1)
 int launch_tile_fast_i16_adpt(const TileArgs &A, cudaStream_t st);
 int launch_tile_fast_u8_adpt(const TileArgs &A, cudaStream_t st);
+// ... with one-byte state planes (ST_U8)
+int launch_tile_fast_i16_s8(const TileArgs &A, cudaStream_t st);
+int launch_tile_fast_u8_s8(const TileArgs &A, cudaStream_t st);
+int launch_tile_fast_i16_adpt_s8(const TileArgs &A, cudaStream_t st);
+int launch_tile_fast_u8_adpt_s8(const TileArgs &A, cudaStream_t st);
 
 }  // namespace dvs

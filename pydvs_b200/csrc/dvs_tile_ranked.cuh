@@ -26,10 +26,11 @@ namespace dvs {
 #define FAST2R_MINB 5
 #endif
 
-template <int SRC, int JH, int ENC>
+template <int SRC, int JH, int ENC, int ST>
 DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigned char *smem_raw) {
   static_assert(ENC == ENC_RATE_CODED || ENC == ENC_TIME_CODED, "inlined encoders only");
   constexpr int J = 2 * JH;
+  using state_t = typename state_elem<ST>::type;
   uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
   uint32_t *wtot = wl + A.fast_cap;
   uint32_t *hist = wtot + 32;
@@ -39,11 +40,11 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
   const int tile = s_idx * A.tiles_per_stream + t_idx;
   const int row0 = t_idx * 2;
   const size_t plane_off = ((size_t)s_idx * A.H + row0) * A.W;
-  int16_t *const ref_t = A.ref + plane_off;
+  state_t *const ref_t = static_cast<state_t *>(A.ref) + plane_off;
   const int gpr = A.W >> 3;  // groups of 8 pixels per row
   const unsigned char *const cur_thread =
       static_cast<const unsigned char *>(A.curr) + (plane_off + (size_t)tid * 8) * (SRC == SRC_U8 ? 1 : 2);
-  const int16_t *const ref_thread = ref_t + tid * 8;
+  const state_t *const ref_thread = ref_t + tid * 8;
 
   // ---- 1. loads: group j = row (j / JH), column block (j % JH); all requests in flight before first use -------------
   uint32_t c_pk[J][4], r_pk[J][4];
@@ -54,20 +55,19 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
   for (int j = 0; j < J; ++j) {
     const int off = (j / JH) * A.W + (j % JH) * (int)blockDim.x * 8;
     if (have[j % JH]) {
-      if (SRC == SRC_U8) {
-        const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(cur_thread + off));
-        c_pk[j][0] = __byte_perm(v.x, 0, 0x4140); c_pk[j][1] = __byte_perm(v.x, 0, 0x4342);
-        c_pk[j][2] = __byte_perm(v.y, 0, 0x4140); c_pk[j][3] = __byte_perm(v.y, 0, 0x4342);
-      } else {
-        const uint4 v = ld16_stream(cur_thread + 2 * off);
-        c_pk[j][0] = v.x; c_pk[j][1] = v.y; c_pk[j][2] = v.z; c_pk[j][3] = v.w;
-      }
-      const uint4 r = ld16(ref_thread + off);
-      r_pk[j][0] = r.x; r_pk[j][1] = r.y; r_pk[j][2] = r.z; r_pk[j][3] = r.w;
+      ld8_raw<(SRC == SRC_U8 ? 1 : 2), true>(cur_thread + (SRC == SRC_U8 ? 1 : 2) * off, c_pk[j]);
+      ld8_raw<(ST == ST_U8 ? 1 : 2), false>(ref_thread + off, r_pk[j]);
     }
   }
   if (tid < 2 * nh) hist[tid] = 0;
   for (int i = blockDim.x + tid; i < 2 * nh; i += blockDim.x) hist[i] = 0;
+  // bytes -> 16-bit lanes only after every load has been issued (see ld8_raw)
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    if (!have[j % JH]) continue;
+    widen8<(SRC == SRC_U8 ? 1 : 2)>(c_pk[j]);
+    widen8<(ST == ST_U8 ? 1 : 2)>(r_pk[j]);
+  }
 
   // ---- 2. threshold + 2x2 inhibition + finished entries + class counts ----------------------------------------------
   const int T = A.thr_scalar;                                  // 2 <= T <= 32767 (host-checked)
@@ -84,7 +84,8 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
 #pragma unroll
     for (int w = 0; w < 4; ++w) wle[h][w] = 0u;
     if (!have[h]) continue;
-    rng |= ((r_pk[ju][0] | r_pk[ju][1] | r_pk[ju][2]) | r_pk[ju][3]) | ((r_pk[jl][0] | r_pk[jl][1] | r_pk[jl][2]) | r_pk[jl][3]);
+    if (ST != ST_U8)  // one-byte state cannot leave [0, 255]
+      rng |= ((r_pk[ju][0] | r_pk[ju][1] | r_pk[ju][2]) | r_pk[ju][3]) | ((r_pk[jl][0] | r_pk[jl][1] | r_pk[jl][2]) | r_pk[jl][3]);
     if (SRC != SRC_U8)
       rng |= ((c_pk[ju][0] | c_pk[ju][1] | c_pk[ju][2]) | c_pk[ju][3]) | ((c_pk[jl][0] | c_pk[jl][1] | c_pk[jl][2]) | c_pk[jl][3]);
     const uint32_t qu = (uint32_t)(h * (int)blockDim.x * 8 + tid * 8);
@@ -184,7 +185,7 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
           // silent spike: its only effect is the reference update (gs:244-249), done right here by the owner thread
           const int r = (e >> 13) & 0xff, a = (e >> 21) & 0xff;
           const int upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;
-          ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
+          ref_t[q] = (state_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
         } else {
           const bool lower = q >= A.W;
           const uint32_t x = lower ? pn[JH + h] : pn[h];
@@ -217,7 +218,7 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
     const bool neg = (e >> 29) & 1u;
     const int y = q >= A.W ? 1 : 0, x = q - (y ? A.W : 0);
     const int upd = min((int)__umulhi((unsigned)a, magic), max_n) * T;  // gs:244-249
-    ref_t[q] = (int16_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
+    ref_t[q] = (state_t)(neg ? max(r - upd, 0) : min(r + upd, 255));
     int desc;
     if (ENC == ENC_RATE_CODED) {
       desc = max(0, (A.enc.n_slots - 1) - (int)__umulhi((unsigned)a, A.enc.dv.magic));  // k, gs:830-832
@@ -242,15 +243,15 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
   write_counters(A, s_idx, t_idx, hist, nh, n_pos, n_neg);
 }
 
-template <int SRC, int JH, int ENC>
+template <int SRC, int JH, int ENC, int ST = ST_I16>
 __global__ void __launch_bounds__(256, FAST2R_MINB) k_tile_ranked(const __grid_constant__ TileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_trigger();
-  fast2r_tile<SRC, JH, ENC>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw);
+  fast2r_tile<SRC, JH, ENC, ST>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw);
 }
 
 // Caller guarantees the FUSED2 shape (see dispatch_fast_shapes) and two-row tiles of at most 8192 pixels.
-template <int SRC, int JH, int ENC>
+template <int SRC, int JH, int ENC, int ST>
 static int launch_ranked(const TileArgs &A_in, int bd, cudaStream_t st) {
   TileArgs A = A_in;
   A.inv_nw = (65536u + (unsigned)(bd / 32) - 1u) / (unsigned)(bd / 32);
@@ -260,7 +261,7 @@ static int launch_ranked(const TileArgs &A_in, int bd, cudaStream_t st) {
   A.fast_cap = fast_cap_of(A);
   const size_t smem = (size_t)A.fast_cap * 4 + (32 + 2 * nh + 4) * sizeof(uint32_t);
   cudaError_t e;
-  k_tile_ranked<SRC, JH, ENC><<<dim3((unsigned)A.tiles_per_stream, (unsigned)A.S), bd, smem, st>>>(A);
+  k_tile_ranked<SRC, JH, ENC, ST><<<dim3((unsigned)A.tiles_per_stream, (unsigned)A.S), bd, smem, st>>>(A);
   if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
   // generic body over the (normally zero) declined tiles
   auto kr = k_tile_redo<SRC, 4, INH_K2, false>;

@@ -172,7 +172,7 @@ class DVSStreams:
 
     def __init__(self, cfg: DVSConfig, device=None, event_capacity: Optional[int] = None,
                  debug_planes: bool = False, force_generic: bool = False, pipeline_depth: int = 1,
-                 split_lists: bool = True, graph="auto"):
+                 split_lists: bool = True, graph="auto", state_dtype: str = "int16"):
         if not torch.cuda.is_available():
             raise RuntimeError("pydvs_b200 needs a CUDA device (there is no CPU path)")
         self.cfg = cfg = cfg.resolved()
@@ -199,12 +199,29 @@ class DVSStreams:
         self.rec_stride = (tr // k) * (self.W // k) if k > 1 else self.tile_px
         self.C = 2 + 2 * self.n_slots
         dev = self.device
-        # state
-        self.ref = torch.full((self.S, self.H, self.W), cfg.ref0, dtype=torch.int16, device=dev)
-        self.thr = None
+        # state.  "int16": the planes as the reference's API holds them (``ref`` / ``thr`` ARE the resident tensors).
+        # "uint8": one byte per pixel -- every update rule clips the reference to [0, 255] (gs:251, 297, 378, 425) and
+        # the coded threshold rule to [min, max] (gs:297), so for a start inside [0, 255] the bytes hold the reference's
+        # own values and a step moves half the state bytes (``ref`` / ``thr`` then return int16 COPIES; write with
+        # set_state()).  "auto": uint8 whenever that is exact for this configuration.
+        t0 = cfg.threshold if cfg.threshold0 is None else cfg.threshold0
+        compact_ok = (0 <= int(cfg.ref0) <= 255 and not debug_planes and
+                      (not cfg.adaptive_threshold or
+                       (not cfg.uncoded and 0 <= int(cfg.min_threshold) <= int(cfg.max_threshold) <= 255
+                        and 0 <= int(t0) <= 255)))
+        if state_dtype == "auto":
+            state_dtype = "uint8" if compact_ok else "int16"
+        if state_dtype not in ("int16", "uint8"):
+            raise ValueError("state_dtype must be 'int16', 'uint8' or 'auto'")
+        if state_dtype == "uint8" and not compact_ok:
+            raise ValueError("one-byte state needs ref0 (and threshold0, min/max_threshold of the coded adaptive rule) in "
+                             "[0, 255] and no debug planes")
+        self.state_dtype = state_dtype
+        sdt = torch.uint8 if state_dtype == "uint8" else torch.int16
+        self._ref = torch.full((self.S, self.H, self.W), cfg.ref0, dtype=sdt, device=dev)
+        self._thr = None
         if cfg.adaptive_threshold:
-            t0 = cfg.threshold if cfg.threshold0 is None else cfg.threshold0
-            self.thr = torch.full((self.S, self.H, self.W), t0, dtype=torch.int16, device=dev)
+            self._thr = torch.full((self.S, self.H, self.W), t0, dtype=sdt, device=dev)
         # LUT (time-binary modes)
         self.lut = None
         if self.enc_mode in (_lib.ENC_TIME_BIN, _lib.ENC_TIME_BIN_THR) or self.upd_mode in (
@@ -259,6 +276,31 @@ class DVSStreams:
         self._graphs = {}          # frame buffer address -> captured step
         self._graph_misses = 0
 
+    # state planes as int16 (the reference's dtype): the resident tensors themselves, or copies of the one-byte state
+    ref = property(lambda self: self._ref if self._ref.dtype == torch.int16 else self._ref.to(torch.int16))
+    thr = property(lambda self: None if self._thr is None else
+                   (self._thr if self._thr.dtype == torch.int16 else self._thr.to(torch.int16)))
+
+    def ref_plane(self, s):
+        """Reference plane of stream ``s`` as int16 [H, W] (a copy when the state is held in bytes)."""
+        return self._ref[s].to(torch.int16)
+
+    def thr_plane(self, s):
+        return None if self._thr is None else self._thr[s].to(torch.int16)
+
+    def set_state(self, ref=None, thr=None):
+        """Overwrite the reference and / or threshold planes (int16 values; with one-byte state they must lie in
+        [0, 255], which is where every update rule leaves them)."""
+        for dst, src, name in ((self._ref, ref, "ref"), (self._thr, thr, "thr")):
+            if src is None:
+                continue
+            if dst is None:
+                raise ValueError("no %s plane in this configuration" % name)
+            src = torch.as_tensor(src, device=self.device)
+            if dst.dtype == torch.uint8 and src.dtype != torch.uint8 and (int(src.min()) < 0 or int(src.max()) > 255):
+                raise ValueError("%s values outside [0, 255] cannot be held in one-byte state" % name)
+            dst.copy_(src.reshape(dst.shape))
+
     # the buffer set of the most recent step
     records = property(lambda self: self._sets[self._cur]["records"])
     tile_counts = property(lambda self: self._sets[self._cur]["tile_counts"])
@@ -289,8 +331,9 @@ class DVSStreams:
         p.drop_silent = int(not self.split_lists)
         p.record_stride = self.rec_stride
         p.enc = self._enc
-        p.ref = self.ref.data_ptr()
-        p.thr = self.thr.data_ptr() if self.thr is not None else None
+        p.state_dtype = _lib.STATE_U8 if self.state_dtype == "uint8" else _lib.STATE_I16
+        p.ref = self._ref.data_ptr()
+        p.thr = self._thr.data_ptr() if self._thr is not None else None
         if self.debug:
             p.diff_out, p.abs_diff_out, p.spikes_out = (self.debug[n].data_ptr() for n in ("diff", "abs_diff", "spikes"))
         p.status, p.redo = self.status.data_ptr(), self.redo.data_ptr()   # records / tile_counts: set per step
@@ -400,14 +443,14 @@ class DVSStreams:
             # warm-up outside the capture (function attributes, lazy module load) on a snapshot of the state, so
             # that capturing leaves ref / thr / frames_done exactly as they were: replaying the first frame
             # afterwards applies it once, not twice
-            keep = (self.ref.clone(), None if self.thr is None else self.thr.clone())
+            keep = (self._ref.clone(), None if self._thr is None else self._thr.clone())
             use_graph, self.use_graph = self.use_graph, False
             self.step(frames)
             self.use_graph = use_graph
             torch.cuda.synchronize()
-            self.ref.copy_(keep[0])
-            if self.thr is not None:
-                self.thr.copy_(keep[1])
+            self._ref.copy_(keep[0])
+            if self._thr is not None:
+                self._thr.copy_(keep[1])
             self.status.zero_()
             self.frames_done = 0
         self._graph, self._graph_frames = self._capture_step(frames)[0], frames

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), "libpydvs_b200.so does not export %s" % n
     assert set(_lib.EXPORTS) == set(names), "ctypes binding and header disagree"
-    assert _lib.lib.dvs_abi_version() == _lib.ABI_VERSION == 3
+    assert _lib.lib.dvs_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_struct_layouts_match_the_header():
@@ -224,7 +224,7 @@ def test_bench_frame_generators_agree_and_the_reference_arm_never_loads_the_prod
     import argparse
     import json
     ref_cfg = json.loads(out.stdout.strip().splitlines()[-1])
-    args = argparse.Namespace(streams=None, scaling="strong", workload="vga_rate_inhibition", pattern="bar",
+    args = argparse.Namespace(streams=None, state_dtype="auto", scaling="strong", workload="vga_rate_inhibition", pattern="bar",
                               frame_dtype="int16", ring=16, settle=2)
     assert ref_cfg == bench.bench_config(args, bench.WORKLOADS["vga_rate_inhibition"], 1)   # both arms print this dict
 

@@ -36,12 +36,14 @@ def _check_event_properties(dvs, res, W, H):
         assert np.all(sizes[:, 1:, :] <= sizes[:, :-1, :])
 
 
-def test_4k_full_pipeline_properties_and_kernel_agreement():
+@pytest.mark.parametrize("state_dtype", ["int16", "uint8"])
+def test_4k_full_pipeline_properties_and_kernel_agreement(state_dtype):
     from oracle import oracle as orc
     from pydvs_b200 import DVSConfig, DVSStreams, synth
     S, H, W = 3, 2160, 3840
     cfg = DVSConfig(width=W, height=H, streams=S, output_type="RATE", threshold=12, max_time_ms=8, inh_area_width=2)
-    fast, generic = DVSStreams(cfg, event_capacity=S * H * W), DVSStreams(cfg, event_capacity=S * H * W, force_generic=True)
+    fast = DVSStreams(cfg, event_capacity=S * H * W, state_dtype=state_dtype)
+    generic = DVSStreams(cfg, event_capacity=S * H * W, force_generic=True)   # int16 state, generic body
     pipe = orc.Pipeline(W, H, mode=orc.ENC_RATE, threshold=12, max_time_ms=8, inh_k=2, flag_shift=15, data_shift=12,
                         data_mask=255)
     for t in range(4):
@@ -60,13 +62,14 @@ def test_4k_full_pipeline_properties_and_kernel_agreement():
     assert res.total_events() == 0 and torch.equal(fast.ref, before)
 
 
-def test_1080p_time_adaptive_properties():
+@pytest.mark.parametrize("state_dtype", ["int16", "uint8"])
+def test_1080p_time_adaptive_properties(state_dtype):
     from oracle import oracle as orc
     from pydvs_b200 import DVSConfig, DVSStreams, synth
     S, H, W = 3, 1080, 1920
     cfg = DVSConfig(width=W, height=H, streams=S, output_type="TIME", threshold=12, adaptive_threshold=True, max_time_ms=4,
                     num_bins=4, threshold0=12)
-    dvs = DVSStreams(cfg, event_capacity=S * H * W)
+    dvs = DVSStreams(cfg, event_capacity=S * H * W, state_dtype=state_dtype)
     pipe = orc.Pipeline(W, H, mode=orc.ENC_TIME, threshold=12, max_time_ms=4, num_bins=4, adaptive=True, min_thr=6,
                         max_thr=168, down=2, up=12, flag_shift=15, data_shift=11, data_mask=255, thr0=12)
     for t in range(4):
@@ -96,8 +99,9 @@ def test_float_mode_4k_linearity_of_quiet_pixels():
     assert torch.all(op.ref == 8.0) and torch.all(op.diff == 0) and torch.all(op.thr == 1e9)
 
 
+@pytest.mark.parametrize("state_dtype", ["int16", "uint8"])
 @pytest.mark.parametrize("workload", ["4k_rate_inhibition", "1080p_time_adaptive", "4k_dense"])
-def test_repeated_steps_are_byte_identical(workload):
+def test_repeated_steps_are_byte_identical(workload, state_dtype):
     """Determinism stress (stands in for racecheck, which is closed on this pool): the same multi-stream step from the
     same state, 50 times, must produce byte-identical events, CSR row pointers, reference and threshold planes --
     shared-memory histograms, atomics into the redo list and the ordered compaction leave no room for run-to-run order."""
@@ -110,7 +114,7 @@ def test_repeated_steps_are_byte_identical(workload):
         S, H, W = 16, 2160, 3840
         cfg = DVSConfig(width=W, height=H, streams=S, output_type="RATE", max_time_ms=8, inh_area_width=2)
     pattern = "dense" if workload == "4k_dense" else "bar"
-    dvs = DVSStreams(cfg, event_capacity=S * H * W * (2 if pattern == "dense" else 1), graph=False)
+    dvs = DVSStreams(cfg, event_capacity=S * H * W * (2 if pattern == "dense" else 1), graph=False, state_dtype=state_dtype)
     for t in range(6):     # leave the start-up transient (the generic body handles its overfull tiles) but keep spikes
         dvs.step(synth.hashed_frames(S, H, W, t, pattern=pattern))
     frame = synth.hashed_frames(S, H, W, 6, pattern=pattern)
@@ -118,9 +122,7 @@ def test_repeated_steps_are_byte_identical(workload):
     thr0 = dvs.thr.clone() if dvs.thr is not None else None
     first = None
     for rep in range(50):
-        dvs.ref.copy_(ref0)
-        if thr0 is not None:
-            dvs.thr.copy_(thr0)
+        dvs.set_state(ref=ref0, thr=thr0)
         res = dvs.step(frame)
         n = res.total_events()
         got = (res.seg_offsets.clone(), res.events_raw[:n].clone(), dvs.ref.clone(),

@@ -18,7 +18,7 @@ def _key_params(W, H):
 def _run_case(S, H, W, *, output_type="RATE", frames=6, source="random", inh=0, adaptive=False, hw=1.0,
               polarity=2, uncoded=False, frame_dtype="int16", threshold=12, max_time_ms=8, num_bins=None,
               thr0=None, tile_rows=None, seed=0, lut_bits=(2, 6), ref0=128, debug=True, force_generic=False,
-              split_lists=True, cfg_extra=None):
+              split_lists=True, cfg_extra=None, state_dtype="int16"):
     from oracle import oracle as orc
     from pydvs_b200 import DVSConfig, DVSStreams, synth
     import pydvs_b200.generate_spikes as gs
@@ -29,7 +29,8 @@ def _run_case(S, H, W, *, output_type="RATE", frames=6, source="random", inh=0, 
                     inh_area_width=inh, uncoded=uncoded, frame_dtype=frame_dtype, log2_table=lut,
                     threshold0=thr0, tile_rows=tile_rows, ref0=ref0, **(cfg_extra or {}))
     dvs = DVSStreams(cfg, debug_planes=debug, event_capacity=S * H * W * max(8, max_time_ms),
-                     force_generic=force_generic, split_lists=split_lists)
+                     force_generic=force_generic, split_lists=split_lists, state_dtype=state_dtype)
+    assert dvs.state_dtype == state_dtype and dvs._ref.dtype == (torch.uint8 if state_dtype == "uint8" else torch.int16)
     rc = dvs.cfg
     fs, ds, dm = _key_params(W, H)
     pipes = [orc.Pipeline(W, H, mode=ENC[output_type], threshold=threshold, max_time_ms=rc.max_time_ms,
