@@ -494,7 +494,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   }
   if (ADAPT && !TLATE && !THR_EARLY) store_thresholds();
   if (decay) store_decayed_reference();
-  {
+  if (w_any) {  // (a warp without candidates has nothing to push)
     // entry: tile-local pixel index (13 bits) | reference << 13 (8 bits) | abs_diff << 21 (8 bits) | negative << 29
     const uint32_t ex_lo = in_lo - cnt_lo, ex_hi = in_hi - cnt_hi;
     auto entry_of = [&](int q, int c, int r) -> uint32_t {

@@ -25,6 +25,10 @@ namespace dvs {
 #ifndef FAST2R_MINB
 #define FAST2R_MINB 5
 #endif
+#ifndef RANKED_QUIET_SKIP
+#define RANKED_QUIET_SKIP 0   // one early-out per 2 x 8 block ahead of the per-area loop: the flag pass keeps its differences
+                              // alive (60 B of spills at 48 registers), K1 at 64 x 4K 0.393 ms against 0.364 without
+#endif
 
 template <int SRC, int JH, int ENC, int ST>
 DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigned char *smem_raw) {
@@ -89,6 +93,17 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
     if (SRC != SRC_U8)
       rng |= ((c_pk[ju][0] | c_pk[ju][1] | c_pk[ju][2]) | c_pk[ju][3]) | ((c_pk[jl][0] | c_pk[jl][1] | c_pk[jl][2]) | c_pk[jl][3]);
     const uint32_t qu = (uint32_t)(h * (int)blockDim.x * 8 + tid * 8);
+#if RANKED_QUIET_SKIP
+    {  // most 2 x 8 blocks of a frame hold no spike at all: one branch for the block instead of one per area
+      uint32_t any = 0u;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t cu = c_pk[ju][w], ru = r_pk[ju][w], cl = c_pk[jl][w], rl = r_pk[jl][w];
+        any |= ((__vmaxu2(cu, ru) - __vminu2(cu, ru)) + kadd) | ((__vmaxu2(cl, rl) - __vminu2(cl, rl)) + kadd);
+      }
+      if ((any & 0x80008000u) == 0u) continue;
+    }
+#endif
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const uint32_t cu = c_pk[ju][w], ru = r_pk[ju][w], cl = c_pk[jl][w], rl = r_pk[jl][w];
@@ -120,7 +135,8 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
   uint32_t inc[JH];
 #pragma unroll
   for (int h = 0; h < JH; ++h) inc[h] = cnt[h];
-  if (__any_sync(kFull, (cnt[0] | cnt[JH - 1]) != 0u)) {
+  const bool w_cand = __any_sync(kFull, (cnt[0] | cnt[JH - 1]) != 0u);
+  if (w_cand) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
@@ -161,7 +177,7 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
   }
   const unsigned magic = A.upd.div_thr.magic;
   const int max_n = A.upd.max_time_ms;
-  {
+  if (w_cand || w_silent) {  // (on sparse frames most warps of a tile hold no winner at all)
     // pn[j]: next pos rank | next neg work-list position << 16 of this thread in group j
     uint32_t pn[J];
 #pragma unroll

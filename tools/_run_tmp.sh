@@ -1,15 +1,12 @@
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo rc=$? >> gpurun_out/pytest.log; tail -4 gpurun_out/pytest.log
-OUT=gpurun_out/s3f; mkdir -p $OUT
-P="--no-e2e --no-cpu-baseline --no-parity --configs none --steps 20 --warmup 5"
-for sd in int16 uint8; do
-python bench.py $P --state-dtype $sd > $OUT/cfg5_$sd.json 2>$OUT/cfg5_$sd.err
-python bench.py $P --state-dtype $sd --frame-dtype uint8 > $OUT/cfg5_u8f_$sd.json 2>$OUT/cfg5_u8f_$sd.err
-python bench.py $P --state-dtype $sd --pattern dense --settle 2 --ring 4 > $OUT/dense_$sd.json 2>$OUT/dense_$sd.err
-python bench.py $P --state-dtype $sd --workload 1080p_time_adaptive --settle 8 --ring 4 > $OUT/cfg4_$sd.json 2>$OUT/cfg4_$sd.err
-python bench.py $P --state-dtype $sd --workload 1080p_time_adaptive --settle 8 --ring 4 --frame-dtype uint8 > $OUT/cfg4_u8f_$sd.json 2>$OUT/cfg4_u8f_$sd.err
-python bench.py $P --state-dtype $sd --streams 32 > $OUT/cfg5_s32_$sd.json 2>$OUT/cfg5_s32_$sd.err
-done
-for f in $OUT/*.json; do echo $f; python -c "
-import json,sys
-d=json.loads(open('$f').read().strip().splitlines()[-1]); r=d['roofline']
-print(d['ms_per_step'], r['k1_ms'], r.get('scan_expand_ms'), r['state_dtype'], d['details']['events_last_step'])"; done
+OUT=gpurun_out/s3h; mkdir -p $OUT
+  B="--no-e2e --no-cpu-baseline --no-parity --configs none --steps 20 --warmup 3 --ring 8"
+  for W in "--streams 64" "--streams 64 --pattern dense --settle 2" "--streams 64 --frame-dtype uint8" "--streams 64 --state-dtype int16" "--workload vga_rate_inhibition --streams 2048" "--workload 1080p_time_adaptive --settle 8" "--workload 4k_rate_no_inhibition --streams 64" "--streams 32"; do
+    python bench.py $B $W 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1]); r = d['roofline']
+print(json.dumps({'lib': 'main', 'args': '$W', 'ms': round(d['ms_per_step'], 4), 'k1_ms': round(r['k1_ms'], 4), 'frac': round(r['frac'], 3), 'events': d['details']['events_last_step']}))" >> $OUT/sweep.jsonl
+  done
+cat $OUT/sweep.jsonl
+python bench.py --no-e2e --no-cpu-baseline --no-parity --configs none --steps 5 --warmup 3 > $OUT/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 500 --csv --log-file $OUT/launches_default_s256.csv python bench.py --no-e2e --no-cpu-baseline --no-parity --configs none --steps 5 --warmup 3 > $OUT/ncu_launches.log 2>&1
+tail -n 8 $OUT/launches_default_s256.csv | cut -c1-200
