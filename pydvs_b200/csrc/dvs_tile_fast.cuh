@@ -893,7 +893,10 @@ static int launch_fast4(const TileArgs &A_in, cudaStream_t st) {
 #ifndef FAST2_RANKED
 #define FAST2_RANKED 1
 #endif
-template <int SRC, int JH, int ENC, int ST>
+#ifndef RANKED_BD512
+#define RANKED_BD512 0
+#endif
+template <int SRC, int JH, int ENC, int ST, int BD>
 static int launch_ranked(const TileArgs &A_in, int bd, cudaStream_t st);
 
 // Caller guarantees: vec_ok (incl. the threshold plane when ADAPT), W % 8 == 0, <= 1024 groups per tile, inhibition
@@ -931,10 +934,15 @@ static int dispatch_fast_shapes(const TileArgs &A, cudaStream_t st) {
   if constexpr (FAST2_RANKED && !ADAPT) {
     if (enc != ENC_ANY && A.use_staged == 0) {
       if (gpr <= 256)
-        return enc == ENC_RATE_CODED ? launch_ranked<SRC, 1, ENC_RATE_CODED, ST>(A, round32(gpr), st)
-                                     : launch_ranked<SRC, 1, ENC_TIME_CODED, ST>(A, round32(gpr), st);
-      return enc == ENC_RATE_CODED ? launch_ranked<SRC, 2, ENC_RATE_CODED, ST>(A, round32((gpr + 1) / 2), st)
-                                   : launch_ranked<SRC, 2, ENC_TIME_CODED, ST>(A, round32((gpr + 1) / 2), st);
+        return enc == ENC_RATE_CODED ? launch_ranked<SRC, 1, ENC_RATE_CODED, ST, 256>(A, round32(gpr), st)
+                                     : launch_ranked<SRC, 1, ENC_TIME_CODED, ST, 256>(A, round32(gpr), st);
+      if constexpr (RANKED_BD512 && ST == ST_U8) {
+        if (gpr <= 512)
+          return enc == ENC_RATE_CODED ? launch_ranked<SRC, 1, ENC_RATE_CODED, ST, 512>(A, round32(gpr), st)
+                                       : launch_ranked<SRC, 1, ENC_TIME_CODED, ST, 512>(A, round32(gpr), st);
+      }
+      return enc == ENC_RATE_CODED ? launch_ranked<SRC, 2, ENC_RATE_CODED, ST, 256>(A, round32((gpr + 1) / 2), st)
+                                   : launch_ranked<SRC, 2, ENC_TIME_CODED, ST, 256>(A, round32((gpr + 1) / 2), st);
     }
   }
   if (gpr <= 256) return DVS_LAUNCH_ENC(1, true, round32(gpr));

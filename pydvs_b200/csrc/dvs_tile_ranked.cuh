@@ -25,6 +25,25 @@ namespace dvs {
 #ifndef FAST2R_MINB
 #define FAST2R_MINB 5
 #endif
+#ifndef RANKED_LAZY_WIDEN
+#define RANKED_LAZY_WIDEN 1   // one-byte planes stay packed in registers (2 per group instead of 4) and a word is widened where it
+                              // is used: 40 registers without spills, i.e. 6 CTAs per SM.  K1 ms at 64 x 4K (gpurun sweep): 0.336
+                              // against 0.360 (eager, 5 CTAs), 0.344 (eager, 6 CTAs, 8 B of spills), 0.351 (lazy, 5 CTAs);
+                              // uint8 frames 0.325 / 0.355, 2048 x VGA 0.679 / 0.735, dense 4K 0.709 / 0.697
+#endif
+#ifndef FAST2R_MINB_S8
+#define FAST2R_MINB_S8 6      // CTAs per SM asked of ptxas for one-byte state (int16 frames)
+#endif
+#ifndef FAST2R_MINB_S8U8
+#define FAST2R_MINB_S8U8 8    // ... with uint8 frames as well (32 registers, 4 B of spills): 256 x 4K 1.190 ms against 1.254 at 6
+#endif
+#ifndef RANKED_BD512
+#define RANKED_BD512 0        // rows of 257..512 groups as ONE column block per thread in CTAs of 512 threads (one-byte state)
+                              // -- 32 registers, 64 warps per SM, and slower: 64 x 4K K1 0.417 ms against 0.336 (16 warps per barrier)
+#endif
+#ifndef FAST2R_MINB_512
+#define FAST2R_MINB_512 4
+#endif
 #ifndef RANKED_QUIET_SKIP
 #define RANKED_QUIET_SKIP 0   // one early-out per 2 x 8 block ahead of the per-area loop: the flag pass keeps its differences
                               // alive (60 B of spills at 48 registers), K1 at 64 x 4K 0.393 ms against 0.364 without
@@ -34,6 +53,8 @@ template <int SRC, int JH, int ENC, int ST>
 DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigned char *smem_raw) {
   static_assert(ENC == ENC_RATE_CODED || ENC == ENC_TIME_CODED, "inlined encoders only");
   constexpr int J = 2 * JH;
+  constexpr bool LAZY_R = RANKED_LAZY_WIDEN && ST == ST_U8;                  // reference bytes stay packed
+  constexpr bool LAZY_C = RANKED_LAZY_WIDEN && ST == ST_U8 && SRC == SRC_U8;  // ... and the frame bytes
   using state_t = typename state_elem<ST>::type;
   uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
   uint32_t *wtot = wl + A.fast_cap;
@@ -69,9 +90,17 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     if (!have[j % JH]) continue;
-    widen8<(SRC == SRC_U8 ? 1 : 2)>(c_pk[j]);
-    widen8<(ST == ST_U8 ? 1 : 2)>(r_pk[j]);
+    if (!LAZY_C) widen8<(SRC == SRC_U8 ? 1 : 2)>(c_pk[j]);
+    if (!LAZY_R) widen8<(ST == ST_U8 ? 1 : 2)>(r_pk[j]);
   }
+  auto r_word = [&](int j, int w) -> uint32_t {
+    if (LAZY_R) return __byte_perm(r_pk[j][w >> 1], 0, (w & 1) ? 0x4342 : 0x4140);
+    return r_pk[j][w];
+  };
+  auto c_word = [&](int j, int w) -> uint32_t {
+    if (LAZY_C) return __byte_perm(c_pk[j][w >> 1], 0, (w & 1) ? 0x4342 : 0x4140);
+    return c_pk[j][w];
+  };
 
   // ---- 2. threshold + 2x2 inhibition + finished entries + class counts ----------------------------------------------
   const int T = A.thr_scalar;                                  // 2 <= T <= 32767 (host-checked)
@@ -106,7 +135,7 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
 #endif
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-      const uint32_t cu = c_pk[ju][w], ru = r_pk[ju][w], cl = c_pk[jl][w], rl = r_pk[jl][w];
+      const uint32_t cu = c_word(ju, w), ru = r_word(ju, w), cl = c_word(jl, w), rl = r_word(jl, w);
       const uint32_t au = __vmaxu2(cu, ru) - __vminu2(cu, ru), al = __vmaxu2(cl, rl) - __vminu2(cl, rl);
       const uint32_t fu = (au + kadd) & 0x80008000u, fl2 = (al + kadd) & 0x80008000u;  // thresholded_difference gs:67-78
       if ((fu | fl2) == 0u) continue;
@@ -259,15 +288,16 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
   write_counters(A, s_idx, t_idx, hist, nh, n_pos, n_neg);
 }
 
-template <int SRC, int JH, int ENC, int ST = ST_I16>
-__global__ void __launch_bounds__(256, FAST2R_MINB) k_tile_ranked(const __grid_constant__ TileArgs A) {
+template <int SRC, int JH, int ENC, int ST = ST_I16, int BD = 256>
+__global__ void __launch_bounds__(BD, BD == 512 ? FAST2R_MINB_512 : ST == ST_U8 ? (SRC == SRC_U8 ? FAST2R_MINB_S8U8 : FAST2R_MINB_S8) : FAST2R_MINB)
+    k_tile_ranked(const __grid_constant__ TileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_trigger();
   fast2r_tile<SRC, JH, ENC, ST>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw);
 }
 
 // Caller guarantees the FUSED2 shape (see dispatch_fast_shapes) and two-row tiles of at most 8192 pixels.
-template <int SRC, int JH, int ENC, int ST>
+template <int SRC, int JH, int ENC, int ST, int BD = 256>
 static int launch_ranked(const TileArgs &A_in, int bd, cudaStream_t st) {
   TileArgs A = A_in;
   A.inv_nw = (65536u + (unsigned)(bd / 32) - 1u) / (unsigned)(bd / 32);
@@ -277,7 +307,7 @@ static int launch_ranked(const TileArgs &A_in, int bd, cudaStream_t st) {
   A.fast_cap = fast_cap_of(A);
   const size_t smem = (size_t)A.fast_cap * 4 + (32 + 2 * nh + 4) * sizeof(uint32_t);
   cudaError_t e;
-  k_tile_ranked<SRC, JH, ENC, ST><<<dim3((unsigned)A.tiles_per_stream, (unsigned)A.S), bd, smem, st>>>(A);
+  k_tile_ranked<SRC, JH, ENC, ST, BD><<<dim3((unsigned)A.tiles_per_stream, (unsigned)A.S), bd, smem, st>>>(A);
   if ((e = cudaGetLastError()) != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
   // generic body over the (normally zero) declined tiles
   auto kr = k_tile_redo<SRC, 4, INH_K2, false>;
