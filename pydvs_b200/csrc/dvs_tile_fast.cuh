@@ -121,6 +121,13 @@ DEV uint32_t bytes_of_flags4(uint32_t n) { return n * 0x10204080u; }
 #ifndef FAST2_QONLY_ADAPT
 #define FAST2_QONLY_ADAPT 0  // index-only work list for the adaptive kernels as well
 #endif
+#ifndef FAST2_LAZY_STATE
+#define FAST2_LAZY_STATE 1   // adaptive thresholds without inhibition on one-byte state: reference / threshold bytes stay packed
+                             // (2 registers per group) and a word is widened where it is used
+#endif
+#ifndef FAST2_MINB_ADPT_S8
+#define FAST2_MINB_ADPT_S8 5
+#endif
 #ifndef FAST2_THR_EARLY
 #define FAST2_THR_EARLY 1    // adaptive thresholds without inhibition: advanced and stored in the threshold pass itself
 #endif
@@ -192,6 +199,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   // hand -- the winner's abs_diff, position and sign all come out of one packed key maximum -- so the push after the
   // scan only stores finished entries
   constexpr bool FUSED2 = FUSED2_SHAPE;
+  constexpr bool LAZY_S = FAST2_LAZY_STATE && ST == ST_U8 && ADAPT && !PAIR && !STAGED && !QUAD;
   uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
   uint16_t *wl16 = reinterpret_cast<uint16_t *>(smem_raw);  // ENC != 0: pixel indices only
   const int cap = STAGED ? kFastCap : A.fast_cap;
@@ -250,10 +258,29 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     if (!have[j]) continue;
-    if (ADAPT) widen8<(ST == ST_U8 ? 1 : 2)>(t_pk[ADAPT ? j : 0]);
+    if (ADAPT && !LAZY_S) widen8<(ST == ST_U8 ? 1 : 2)>(t_pk[ADAPT ? j : 0]);
     widen8<(SRC == SRC_U8 ? 1 : 2)>(c_pk[j]);
-    if (!STAGED) widen8<(ST == ST_U8 ? 1 : 2)>(r_pk[j]);
+    if (!STAGED && !LAZY_S) widen8<(ST == ST_U8 ? 1 : 2)>(r_pk[j]);
   }
+  // word w (two 16-bit lanes) of the reference / threshold group j; LAZY_S widens the packed bytes on the spot
+  auto rw = [&](int j, int w) -> uint32_t {
+    return LAZY_S ? __byte_perm(r_pk[j][w >> 1], 0, (w & 1) ? 0x4342 : 0x4140) : r_pk[j][w];
+  };
+  auto tw = [&](int j, int w) -> uint32_t {
+    return LAZY_S ? __byte_perm(t_pk[ADAPT ? j : 0][w >> 1], 0, (w & 1) ? 0x4342 : 0x4140) : t_pk[ADAPT ? j : 0][w];
+  };
+  // pixel p (0..7) of group j as a value
+  auto r_px = [&](int j, int p) -> int {
+    if (LAZY_S) return (int)((((unsigned long long)r_pk[j][1] << 32 | r_pk[j][0]) >> (8 * p)) & 0xff);
+    const unsigned long long lo = ((unsigned long long)r_pk[j][1] << 32) | r_pk[j][0], hi = ((unsigned long long)r_pk[j][3] << 32) | r_pk[j][2];
+    return (int)(((p < 4 ? lo : hi) >> (16 * (p & 3))) & 0xffff);
+  };
+  auto t_px = [&](int j, int p) -> int {
+    const int jt = ADAPT ? j : 0;
+    if (LAZY_S) return (int)((((unsigned long long)t_pk[jt][1] << 32 | t_pk[jt][0]) >> (8 * p)) & 0xff);
+    const unsigned long long lo = ((unsigned long long)t_pk[jt][1] << 32) | t_pk[jt][0], hi = ((unsigned long long)t_pk[jt][3] << 32) | t_pk[jt][2];
+    return (int)(((p < 4 ? lo : hi) >> (16 * (p & 3))) & 0xffff);
+  };
   if (tid < 2 * nh) hist[tid] = 0;
   for (int i = blockDim.x + tid; i < 2 * nh; i += blockDim.x) hist[i] = 0;
   if (decay)  // DTYPE(history_weight * ref_frame) gs:249 for every possible in-range reference value, exact in fp64
@@ -268,9 +295,9 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   // abs_diff of a word of two pixels, kept only where the pixel spikes (abs_diff * spikes, gs:73-75); recomputed
   // where it is needed instead of being held in registers across the phases
   auto masked_abs = [&](int j, int w) -> uint32_t {
-    const uint32_t c = c_pk[j][w], r = r_pk[j][w];
+    const uint32_t c = c_pk[j][w], r = rw(j, w);
     const uint32_t a = __vmaxu2(c, r) - __vminu2(c, r);
-    const uint32_t f = ADAPT ? ~((t_pk[ADAPT ? j : 0][w] | 0x80008000u) - a) & 0x80008000u : (a + kadd) & 0x80008000u;
+    const uint32_t f = ADAPT ? ~((tw(j, w) | 0x80008000u) - a) & 0x80008000u : (a + kadd) & 0x80008000u;
     return a & ((f >> 15) * 0xffffu);
   };
   // update_reference_rate_adpt gs:291-297 on packed lanes: +up on the lanes of m (pixels that still spike), -down
@@ -332,19 +359,19 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     uint32_t fl[4];
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-      const uint32_t c = c_pk[j][w], r = r_pk[j][w];
+      const uint32_t c = c_pk[j][w], r = rw(j, w);
       const uint32_t a = __vmaxu2(c, r) - __vminu2(c, r);  // no borrow: max >= min lane-wise
-      if (ADAPT) fl[w] = ~((t_pk[j][w] | 0x80008000u) - a) & 0x80008000u;  // a > threshold lane-wise (both < 2^15)
+      if (ADAPT) fl[w] = ~((tw(j, w) | 0x80008000u) - a) & 0x80008000u;  // a > threshold lane-wise (both < 2^15)
       else fl[w] = (a + kadd) & 0x80008000u;                 // spike flags at bits 15 / 31
     }
-    if (ADAPT) tmax = __vmaxu2(tmax, __vmaxu2(__vmaxu2(t_pk[j][0], t_pk[j][1]), __vmaxu2(t_pk[j][2], t_pk[j][3])));
+    if (ADAPT && !LAZY_S) tmax = __vmaxu2(tmax, __vmaxu2(__vmaxu2(t_pk[j][0], t_pk[j][1]), __vmaxu2(t_pk[j][2], t_pk[j][3])));
     if (ST != ST_U8) rng |= (r_pk[j][0] | r_pk[j][1] | r_pk[j][2]) | r_pk[j][3];  // one-byte state cannot leave [0, 255]
     if (SRC != SRC_U8) rng |= (c_pk[j][0] | c_pk[j][1] | c_pk[j][2]) | c_pk[j][3];
     if (fl[0] | fl[1] | fl[2] | fl[3]) flags8[j] = flags4_of(fl[0], fl[1]) | (flags4_of(fl[2], fl[3]) << 4);
     if (THR_EARLY) {
       uint32_t tn[4];
 #pragma unroll
-      for (int w = 0; w < 4; ++w) tn[w] = thr_new(t_pk[ADAPT ? j : 0][w], msb_lane_mask(fl[w]));
+      for (int w = 0; w < 4; ++w) tn[w] = thr_new(tw(j, w), msb_lane_mask(fl[w]));
       st_state8<ST>(thr_t + q0_of(j), tn);
     }
   }
@@ -352,6 +379,8 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
   if (ADAPT) {
     // a negative threshold (bit 15 as an unsigned lane), or -- coded rule -- one so large that th + up leaves int16
     // and wraps negative in the reference (gs:292): the generic body replays those tiles with exact int16 arithmetic
+    // (LAZY_S: bytes, so only th + up can leave int16, and 255 stands in for the largest threshold)
+    if (LAZY_S) tmax = 0x00ff00ffu;
     const uint32_t over = A.upd.uncoded ? tmax : (tmax | (tmax + (uint32_t)A.upd.thr_up * 0x00010001u));
     if (over & 0x80008000u) rng |= 0xFF00u;
   }
@@ -427,10 +456,10 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       // lane masks of the four words from the 8 pixel flags: flag k -> bit 8k + 7 of a word (multiplication), then PRMT
       const uint32_t g01 = bytes_of_flags4(flags8[j] & 0xfu), g23 = bytes_of_flags4(flags8[j] >> 4);
       uint32_t tn[4];
-      tn[0] = thr_new(t_pk[ADAPT ? j : 0][0], prmt<0x9988u>(g01));
-      tn[1] = thr_new(t_pk[ADAPT ? j : 0][1], prmt<0xBBAAu>(g01));
-      tn[2] = thr_new(t_pk[ADAPT ? j : 0][2], prmt<0x9988u>(g23));
-      tn[3] = thr_new(t_pk[ADAPT ? j : 0][3], prmt<0xBBAAu>(g23));
+      tn[0] = thr_new(tw(j, 0), prmt<0x9988u>(g01));
+      tn[1] = thr_new(tw(j, 1), prmt<0xBBAAu>(g01));
+      tn[2] = thr_new(tw(j, 2), prmt<0x9988u>(g23));
+      tn[3] = thr_new(tw(j, 3), prmt<0xBBAAu>(g23));
       st_state8<ST>(thr_t + q0_of(j), tn);
     }
   };
@@ -443,7 +472,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
       uint32_t rn[4];
 #pragma unroll
       for (int w = 0; w < 4; ++w)
-        rn[w] = (uint32_t)tr_lut[r_pk[j][w] & 0xff] | ((uint32_t)tr_lut[(r_pk[j][w] >> 16) & 0xff] << 16);
+        rn[w] = (uint32_t)tr_lut[rw(j, w) & 0xff] | ((uint32_t)tr_lut[(rw(j, w) >> 16) & 0xff] << 16);
       st_state8<ST>(ref_t + q0_of(j), rn);
     }
   };
@@ -487,7 +516,10 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
     if (THR_EARLY) {  // ... which must find the thresholds as they were
 #pragma unroll
       for (int j = 0; j < J; ++j)
-        if (have[j]) st_state8<ST>(thr_t + q0_of(j), t_pk[ADAPT ? j : 0]);
+        if (have[j]) {
+          if (LAZY_S) *reinterpret_cast<uint2 *>(thr_t + q0_of(j)) = make_uint2(t_pk[ADAPT ? j : 0][0], t_pk[ADAPT ? j : 0][1]);
+          else st_state8<ST>(thr_t + q0_of(j), t_pk[ADAPT ? j : 0]);
+        }
     }
     if (tid == 0) A.redo[2 + atomicAdd(A.redo, 1)] = tile;
     return;
@@ -547,11 +579,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
         uint32_t pos = pos_of[j];
         for (uint32_t m = flags8[j]; m; m &= m - 1) {  // candidates only
           const int p = __ffs(m) - 1;
-          if (ADAPT && !TLATE) {
-            const unsigned long long t_lo = ((unsigned long long)t_pk[ADAPT ? j : 0][1] << 32) | t_pk[ADAPT ? j : 0][0],
-                                     t_hi = ((unsigned long long)t_pk[ADAPT ? j : 0][3] << 32) | t_pk[ADAPT ? j : 0][2];
-            wl_thr[pos] = (uint16_t)((p < 4 ? t_lo : t_hi) >> (16 * (p & 3)));
-          }
+          if (ADAPT && !TLATE) wl_thr[pos] = (uint16_t)t_px(j, p);
           wl16[pos++] = (uint16_t)(q0 + p);
         }
       }
@@ -584,15 +612,11 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
         const int q0 = q0_of(j);
         uint32_t pos = pos_of[j];
         const unsigned long long c_lo = ((unsigned long long)c_pk[j][1] << 32) | c_pk[j][0], c_hi = ((unsigned long long)c_pk[j][3] << 32) | c_pk[j][2];
-        const unsigned long long r_lo = ((unsigned long long)r_pk[j][1] << 32) | r_pk[j][0], r_hi = ((unsigned long long)r_pk[j][3] << 32) | r_pk[j][2];
         for (uint32_t m = flags8[j]; m; m &= m - 1) {  // candidates only
           const int p = __ffs(m) - 1;
           const int sh = 16 * (p & 3);
-          const int c = (int)(((p < 4 ? c_lo : c_hi) >> sh) & 0xffff), r = (int)(((p < 4 ? r_lo : r_hi) >> sh) & 0xffff);
-          if (ADAPT) {
-            const unsigned long long t_lo = ((unsigned long long)t_pk[j][1] << 32) | t_pk[j][0], t_hi = ((unsigned long long)t_pk[j][3] << 32) | t_pk[j][2];
-            wl_thr[pos] = (uint16_t)((p < 4 ? t_lo : t_hi) >> sh);
-          }
+          const int c = (int)(((p < 4 ? c_lo : c_hi) >> sh) & 0xffff), r = r_px(j, p);
+          if (ADAPT) wl_thr[pos] = (uint16_t)t_px(j, p);
           wl[pos++] = entry_of(q0 + p, c, r);
         }
       }
@@ -710,7 +734,7 @@ DEV void fast2_tile(const TileArgs &A, const int t_idx, const int s_idx, unsigne
 #define FAST2_MINB_ADPT 4
 #endif
 template <int SRC, int JH, bool PAIR, int ENC, bool ADAPT = false, int ST = ST_I16>
-__global__ void __launch_bounds__(256, ADAPT ? FAST2_MINB_ADPT : FAST2_MINB) k_tile_fast2(const __grid_constant__ TileArgs A) {
+__global__ void __launch_bounds__(256, ADAPT ? (FAST2_LAZY_STATE && ST == ST_U8 && !PAIR ? FAST2_MINB_ADPT_S8 : FAST2_MINB_ADPT) : FAST2_MINB) k_tile_fast2(const __grid_constant__ TileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_trigger();
   fast2_tile<SRC, JH, PAIR, ENC, ADAPT, false, false, ST>(A, (int)blockIdx.x, (int)blockIdx.y, smem_raw, smem_raw + A.fast_cap * 12,

@@ -37,6 +37,10 @@ namespace dvs {
 #ifndef FAST2R_MINB_S8U8
 #define FAST2R_MINB_S8U8 8    // ... with uint8 frames as well (32 registers, 4 B of spills): 256 x 4K 1.190 ms against 1.254 at 6
 #endif
+#ifndef RANKED_NARROW_I16
+#define RANKED_NARROW_I16 0     // int16 frames narrowed to bytes in registers (32 registers with 20 B of spills, 8 CTAs per SM):
+                                // 64 x 4K K1 0.347 ms against 0.336 without
+#endif
 #ifndef RANKED_BD512
 #define RANKED_BD512 0        // rows of 257..512 groups as ONE column block per thread in CTAs of 512 threads (one-byte state)
                               // -- 32 registers, 64 warps per SM, and slower: 64 x 4K K1 0.417 ms against 0.336 (16 warps per barrier)
@@ -54,7 +58,10 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
   static_assert(ENC == ENC_RATE_CODED || ENC == ENC_TIME_CODED, "inlined encoders only");
   constexpr int J = 2 * JH;
   constexpr bool LAZY_R = RANKED_LAZY_WIDEN && ST == ST_U8;                  // reference bytes stay packed
-  constexpr bool LAZY_C = RANKED_LAZY_WIDEN && ST == ST_U8 && SRC == SRC_U8;  // ... and the frame bytes
+  // int16 frames: once the range vote has seen the raw words, a tile that stays here holds only values in [0, 255], so
+  // the frame can be narrowed to bytes in registers as well (2 PRMT per group) -- fewer live registers, more CTAs per SM
+  constexpr bool NARROW_C = RANKED_NARROW_I16 && RANKED_LAZY_WIDEN && ST == ST_U8 && SRC == SRC_I16;
+  constexpr bool LAZY_C = RANKED_LAZY_WIDEN && ST == ST_U8 && (SRC == SRC_U8 || NARROW_C);  // ... and the frame bytes
   using state_t = typename state_elem<ST>::type;
   uint32_t *wl = reinterpret_cast<uint32_t *>(smem_raw);
   uint32_t *wtot = wl + A.fast_cap;
@@ -87,10 +94,15 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
   if (tid < 2 * nh) hist[tid] = 0;
   for (int i = blockDim.x + tid; i < 2 * nh; i += blockDim.x) hist[i] = 0;
   // bytes -> 16-bit lanes only after every load has been issued (see ld8_raw)
+  uint32_t rng0 = 0;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     if (!have[j % JH]) continue;
-    if (!LAZY_C) widen8<(SRC == SRC_U8 ? 1 : 2)>(c_pk[j]);
+    if (NARROW_C) {
+      rng0 |= (c_pk[j][0] | c_pk[j][1]) | (c_pk[j][2] | c_pk[j][3]);
+      c_pk[j][0] = __byte_perm(c_pk[j][0], c_pk[j][1], 0x6420);
+      c_pk[j][1] = __byte_perm(c_pk[j][2], c_pk[j][3], 0x6420);
+    } else if (!LAZY_C) widen8<(SRC == SRC_U8 ? 1 : 2)>(c_pk[j]);
     if (!LAZY_R) widen8<(ST == ST_U8 ? 1 : 2)>(r_pk[j]);
   }
   auto r_word = [&](int j, int w) -> uint32_t {
@@ -109,7 +121,7 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
   uint32_t wle[JH][4];
   uint32_t cnt[JH];  // recorded winners of this thread per column block, 8-bit fields: upper row pos, lower row pos, upper neg, lower neg
   uint32_t sil = 0;  // bit h: a silent winner in column block h
-  uint32_t rng = 0;
+  uint32_t rng = rng0;
 #pragma unroll
   for (int h = 0; h < JH; ++h) {
     const int ju = h, jl = JH + h;
@@ -119,7 +131,7 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
     if (!have[h]) continue;
     if (ST != ST_U8)  // one-byte state cannot leave [0, 255]
       rng |= ((r_pk[ju][0] | r_pk[ju][1] | r_pk[ju][2]) | r_pk[ju][3]) | ((r_pk[jl][0] | r_pk[jl][1] | r_pk[jl][2]) | r_pk[jl][3]);
-    if (SRC != SRC_U8)
+    if (SRC != SRC_U8 && !NARROW_C)
       rng |= ((c_pk[ju][0] | c_pk[ju][1] | c_pk[ju][2]) | c_pk[ju][3]) | ((c_pk[jl][0] | c_pk[jl][1] | c_pk[jl][2]) | c_pk[jl][3]);
     const uint32_t qu = (uint32_t)(h * (int)blockDim.x * 8 + tid * 8);
 #if RANKED_QUIET_SKIP
@@ -289,7 +301,7 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
 }
 
 template <int SRC, int JH, int ENC, int ST = ST_I16, int BD = 256>
-__global__ void __launch_bounds__(BD, BD == 512 ? FAST2R_MINB_512 : ST == ST_U8 ? (SRC == SRC_U8 ? FAST2R_MINB_S8U8 : FAST2R_MINB_S8) : FAST2R_MINB)
+__global__ void __launch_bounds__(BD, BD == 512 ? FAST2R_MINB_512 : ST == ST_U8 ? (SRC == SRC_U8 || RANKED_NARROW_I16 ? FAST2R_MINB_S8U8 : FAST2R_MINB_S8) : FAST2R_MINB)
     k_tile_ranked(const __grid_constant__ TileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_trigger();
