@@ -91,6 +91,9 @@ def parse_args():
                     help="distinct frames resident per stream.  The bar travels W/64 px per frame; a 4-frame ring settles on a "
                          "period-4 orbit of the state that emits ~60x fewer events than video does, so the default keeps 16")
     ap.add_argument("--e2e-steps", type=int, default=16)
+    ap.add_argument("--host-narrow", default="auto", choices=["auto", "on", "off"],
+                    help="e2e: narrow int16 host frames to bytes on the host cores before the copy (exact; HostFeed); auto = "
+                         "time both ways once and keep the faster")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
@@ -865,8 +868,11 @@ def run_ours(args, wl, rank, local_rank, world):
     e2e = None
     if not args.no_e2e:
         pool_pin = {}   # one pinned allocation serves both legs (page-locking runs at ~2 GB/s)
-        e2e = run_e2e(args, case, world, barrier, allmax, "int16" if args.frame_dtype == "int16" else "uint8", pool_pin)
+        e2e = run_e2e(args, case, world, barrier, allmax, "int16" if args.frame_dtype == "int16" else "uint8", pool_pin,
+                      narrow=args.host_narrow)
         if args.frame_dtype == "int16":
+            if args.host_narrow is not False:   # the straight copy of the int16 planes, for comparison
+                e2e["plain_int16_copy"] = run_e2e(args, case, world, barrier, allmax, "int16", pool_pin, narrow=False)
             from pydvs_b200 import DVSConfig, DVSStreams
             cfg2 = DVSConfig(**{**dvs.cfg.__dict__, "frame_dtype": "uint8"})
             case2 = Case.__new__(Case)
@@ -1002,13 +1008,15 @@ def run_ours(args, wl, rank, local_rank, world):
     return 0 if ok else 1
 
 
-def run_e2e(args, case, world, barrier, allmax, frame_dtype, pool_pin):
-    """Same metric through the public API with HOST buffers: every step copies that step's frames from pinned
-    host memory to the device, runs the step, and reads the AER result (CSR row pointers + events) back to
-    pinned host memory.  The host ring holds the same frames in the same order as the device-timed loop, so the
-    event volume is the steady state's.  H2D of step i+1 overlaps compute / D2H of step i."""
+def run_e2e(args, case, world, barrier, allmax, frame_dtype, pool_pin, narrow=False):
+    """Same metric through the public API with HOST buffers (pydvs_b200.HostFeed + DVSStreams.step): every step moves
+    that step's frames from pinned host memory to the device, runs the step, and reads the AER result (CSR row pointers
+    + events) back to pinned host memory.  The host ring holds the same frames in the same order as the device-timed
+    loop.  The feed works two frame sets ahead: while step i runs, set i+1 is on the wire and -- with ``narrow`` --
+    set i+2 is being narrowed from int16 to bytes on the host cores (exact, every value checked; see HostFeed)."""
     import psutil
     import torch
+    from pydvs_b200 import HostFeed
     dvs, S, P, device = case.dvs, case.S, case.P, case.device
     elem = 1 if frame_dtype == "uint8" else 2
     frame_bytes = S * P * elem
@@ -1028,51 +1036,50 @@ def run_e2e(args, case, world, barrier, allmax, frame_dtype, pool_pin):
     # host[k % n_host] holds ring frame k for the next n_host steps (n_host divides the ring length)
     for j in range(n_host):
         host[(case.i + j) % n_host].copy_(case.ring[(case.i + j) % len(case.ring)])
-    dev_in = [torch.empty_like(case.ring[0]) for _ in range(2)]
     off_host = torch.empty(dvs.seg_offsets.shape, dtype=torch.int64).pin_memory()
     # the short host ring replays a few frames over and over (each wrap is a jump of the bar): heavier steps than the
     # resident ring's steady state, so make room for 4x its largest step; an overflow is reported, not fatal
     dvs.reserve_events(min(S * P * 2, int(getattr(case, "peak_events", 0) * 4) + (1 << 20)))
     ev_cap_host = dvs.event_capacity
     ev_host = torch.empty(ev_cap_host, dtype=torch.int64).pin_memory()
-    s_in, s_x = torch.cuda.Stream(device), torch.cuda.Stream(device)
-    use_graph, dvs.use_graph = dvs.use_graph, False   # dev_in alternates; keep the plain launches
+    s_x = torch.cuda.Stream(device)
+    use_graph, dvs.use_graph = dvs.use_graph, False   # the device buffers alternate; keep the plain launches
+    feed = HostFeed(dvs, narrow=narrow, threads=max(1, (os.cpu_count() or 2) // max(world, 1)))
     # plain pinned H2D ceiling of this run (same buffers, same ranks at the same time)
+    probe = torch.empty_like(case.ring[0])
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     reps = 3
-    with torch.cuda.stream(s_in):
-        for r in range(reps):
-            dev_in[r % 2].copy_(host[r % n_host], non_blocking=True)
+    for r in range(reps):
+        probe.copy_(host[r % n_host], non_blocking=True)
     torch.cuda.synchronize()
     barrier()
     h2d_peak = reps * frame_bytes / allmax(time.perf_counter() - t0) / 1e9
+    del probe
+    if narrow == "auto" and frame_dtype == "int16":   # the feed's own calibration (untimed), all ranks at once
+        barrier()
+        feed.narrow = feed._calibrate(host[case.i % n_host])
+        torch.cuda.synchronize()
 
     K = max(1, args.e2e_steps)
     overflow = False
     first = case.i
-    in_done = [torch.cuda.Event() for _ in range(K + 1)]
     x_done = [torch.cuda.Event() for _ in range(K + 1)]
     d2h_total = 0
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
-    with torch.cuda.stream(s_in):
-        dev_in[0].copy_(host[first % n_host], non_blocking=True)
-        in_done[0].record(s_in)
+    tickets = [feed.submit(host[first % n_host])]
+    if K > 1:
+        tickets.append(feed.submit(host[(first + 1) % n_host]))
     for i in range(K):
-        if i + 1 < K:  # prefetch the next step's frames while this step computes
-            with torch.cuda.stream(s_in):
-                if i >= 1:
-                    s_in.wait_event(x_done[i - 1])  # buffer (i+1)%2 was read by step i-1
-                dev_in[(i + 1) % 2].copy_(host[(first + i + 1) % n_host], non_blocking=True)
-                in_done[i + 1].record(s_in)
         with torch.cuda.stream(s_x):
-            s_x.wait_event(in_done[i])
-            dvs.step(dev_in[i % 2])
+            feed.step(tickets[i])
             off_host.copy_(dvs.seg_offsets, non_blocking=True)
             x_done[i].record(s_x)
+        if i + 2 < K:   # two sets ahead: narrowed / copied while this step and the next copy run
+            tickets.append(feed.submit(host[(first + i + 2) % n_host]))
         x_done[i].synchronize()
         n_ev = int(off_host[-1])
         if n_ev > ev_cap_host:
@@ -1083,6 +1090,7 @@ def run_e2e(args, case, world, barrier, allmax, frame_dtype, pool_pin):
     torch.cuda.synchronize()
     barrier()
     secs = allmax(time.perf_counter() - t0)
+    feed.close()
     case.i += K
     dvs.use_graph = use_graph
     try:
@@ -1090,16 +1098,26 @@ def run_e2e(args, case, world, barrier, allmax, frame_dtype, pool_pin):
     except OverflowError:
         overflow = True
     value = bench_config(args, case.wl, world)["streams_total"] * K / secs
-    return {"value": value, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": d2h_total // K,
-            "steps": K, "gpixel_per_s": value * P / 1e9, "host_frame_dtype": frame_dtype, "host_ring_frames": n_host,
-            "pin_seconds": t_pin, "h2d_peak_gbs": h2d_peak, "h2d_achieved_gbs": frame_bytes * K / secs / 1e9,
-            "h2d_frac_of_peak": frame_bytes * K / secs / 1e9 / h2d_peak, "event_overflow": overflow,
-            "note": "per GPU: pinned host frames -> H2D -> fused step -> D2H of CSR offsets + events, every step; "
-                    "h2d_peak_gbs = plain pinned-memory copies of the same buffers with all ranks copying at once"}
+    narrowed = feed.stats["narrowed"]
+    wire_bytes = frame_bytes // 2 if (narrowed == K and frame_dtype == "int16") else frame_bytes
+    out = {"value": value, "unit": "frames/s", "h2d_bytes_per_step": wire_bytes, "d2h_bytes_per_step": d2h_total // K,
+           "steps": K, "gpixel_per_s": value * P / 1e9, "host_frame_dtype": frame_dtype, "host_ring_frames": n_host,
+           "host_frame_bytes_per_step": frame_bytes, "pin_seconds": t_pin, "h2d_peak_gbs": h2d_peak,
+           "h2d_achieved_gbs": wire_bytes * K / secs / 1e9, "h2d_frac_of_peak": wire_bytes * K / secs / 1e9 / h2d_peak,
+           "event_overflow": overflow,
+           "host_narrowing": {"mode": str(narrow), "narrowed_steps": narrowed, "plain_steps": feed.stats["plain"],
+                              "out_of_range_steps": feed.stats["out_of_range"], "threads": feed.threads,
+                              "narrow_seconds_per_step": feed.stats["narrow_seconds"] / max(1, narrowed) if narrowed else None,
+                              "calibration": feed.stats["calibration"]},
+           "note": "per GPU: pinned host frames -> (exact narrowing of int16 planes to bytes on the host cores when that is "
+                   "faster than copying them) -> H2D -> fused step -> D2H of CSR offsets + events, every step; "
+                   "h2d_peak_gbs = plain pinned-memory copies of the same buffers with all ranks copying at once"}
+    return out
 
 
 def main():
     args = parse_args()
+    args.host_narrow = {"auto": "auto", "on": True, "off": False}[args.host_narrow]
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -170,6 +170,12 @@ const char *dvs_last_error_string(void);
 int dvs_get_limits(dvs_limits *out_host);
 /* Host helper: tile_rows for a geometry (multiple of max(inh_k,1), tile_rows*W <= max_tile_px). */
 int dvs_choose_tile_rows(int32_t S, int32_t H, int32_t W, int32_t inh_k);
+/* Host helper for callers whose frames live in HOST memory: the reference hands 8-bit gray values over as int16 planes
+ * (stand_alone.py:160-166 `.astype(int16)`), and a pinned host->device copy is what bounds such a step, so the feed may
+ * narrow a frame to bytes on `threads` host threads (0 = all), copy half the bytes and run the step with
+ * DVS_FRAME_U8.  Exact: *out_of_range is 1 when any value lies outside [0, 255] (copy the int16 plane then).
+ * `dst` 32-byte aligned enables the AVX2 / streaming-store path.  No CUDA call. */
+int dvs_host_narrow_i16_u8(const int16_t *src, uint8_t *dst, int64_t n, int32_t threads, int32_t *out_of_range);
 
 /* ---- unfused, function-for-function kernels (drop-in module API) ------------------------------ */
 

@@ -81,6 +81,7 @@ _SIGNATURES = {
     "dvs_last_error_string": (C.c_char_p, []),
     "dvs_get_limits": (C.c_int, [C.POINTER(Limits)]),
     "dvs_choose_tile_rows": (C.c_int, [_I32, _I32, _I32, _I32]),
+    "dvs_host_narrow_i16_u8": (C.c_int, [_P, _P, _I64, _I32, _P]),
     "dvs_thresholded_difference_i16": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _I64, _P]),
     "dvs_local_inhibition_i16": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
     "dvs_update_reference_i16": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32,

@@ -22,7 +22,7 @@ STAMP = LIB + ".sha256"  # next to the library: travels with it to the GPU box
 UNITS = ["dvs_b200.cu", "tile_pass_i16.cu", "tile_pass_i16_adpt.cu", "tile_pass_u8.cu",
          "tile_pass_u8_adpt.cu", "tile_pass_planes.cu", "tile_fast_i16.cu", "tile_fast_u8.cu",
          "tile_fast_i16_adpt.cu", "tile_fast_u8_adpt.cu", "tile_fast_i16_s8.cu", "tile_fast_u8_s8.cu",
-         "tile_fast_i16_adpt_s8.cu", "tile_fast_u8_adpt_s8.cu", "dvs_next_rows.cu"]
+         "tile_fast_i16_adpt_s8.cu", "tile_fast_u8_adpt_s8.cu", "dvs_next_rows.cu", "dvs_host.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]
 
@@ -58,7 +58,7 @@ def build(force=False, verbose=True, ptxas_verbose=False):
     extra = ["-Xptxas", "-v"] if ptxas_verbose else []
 
     def compile_one(unit):
-        obj = os.path.join(OBJ_DIR, unit.replace(".cu", ".o"))
+        obj = os.path.join(OBJ_DIR, os.path.splitext(unit)[0] + ".o")
         cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, unit), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

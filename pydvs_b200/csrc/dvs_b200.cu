@@ -416,8 +416,11 @@ struct ExpandArgs {
 // NS8 (n_slots <= 8, no time-binary multiplicities): every lane also pre-loads its own task's 8 segment
 // positions (coalesced over tiles) and the first records of the NEXT task are prefetched while the
 // current one is expanded, so the dependent-load chain per task is off the critical path.
+#ifndef EXPAND_MINB
+#define EXPAND_MINB 5   // 48 registers (no spills on the NS8 path); 4 / 6 / 8 measured within 5 us of each other at 256 x 4K
+#endif
 template <bool NS8>
-__global__ void __launch_bounds__(256) k_expand(const __grid_constant__ ExpandArgs A) {
+__global__ void __launch_bounds__(256, EXPAND_MINB) k_expand(const __grid_constant__ ExpandArgs A) {
   pdl_wait();  // the scan (and through it the tile pass) has completed
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.y;

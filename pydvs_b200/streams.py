@@ -343,9 +343,10 @@ class DVSStreams:
     def step(self, frames: torch.Tensor, expand: bool = True) -> StepResult:
         """Advance every stream by one frame.  ``frames``: CUDA tensor [S, H, W] (or [H, W] when
         S == 1) of the configured frame dtype.  Asynchronous: three kernel launches, no host sync."""
-        want = torch.uint8 if self.cfg.frame_dtype == "uint8" else torch.int16
-        if frames.dtype != want or not frames.is_cuda:
-            raise ValueError("frames must be a CUDA tensor of dtype %s" % want)
+        # (an int16 configuration also takes uint8 frames -- the same values in half the bytes, see HostFeed)
+        ok = (torch.uint8,) if self.cfg.frame_dtype == "uint8" else (torch.int16, torch.uint8)
+        if frames.dtype not in ok or not frames.is_cuda:
+            raise ValueError("frames must be a CUDA tensor of dtype %s" % (ok[0],))
         if frames.numel() != self.S * self.P or not frames.is_contiguous():
             raise ValueError("frames must be contiguous with shape [%d, %d, %d]" % (self.S, self.H, self.W))
         if self.use_graph and expand and self.frames_done > 0:   # the first step runs eagerly (module load, attributes)
@@ -421,6 +422,7 @@ class DVSStreams:
     def tile_pass(self, frames):
         """K1: fused threshold / inhibition / state update / record compaction / slot counts."""
         self._params.curr = frames.data_ptr()
+        self._params.frame_dtype = _lib.FRAME_U8 if frames.dtype == torch.uint8 else _lib.FRAME_I16
         self._params.records, self._params.tile_counts = self.records.data_ptr(), self.tile_counts.data_ptr()
         check(lib.dvs_step_fused(C.byref(self._params), current_stream_ptr()))
         self.kernel_path = lib.dvs_last_step_path()   # _lib.PATH_*: which tile kernel ran (generic body or a fast path)

@@ -245,3 +245,29 @@ def test_bench_parity_job_detects_a_flipped_pixel():
     assert r["ref_equal"] and r["events_equal"] and r["thr_equal"]
     job["ref"][5, 7] ^= 1
     assert not bench.run_parity_job(job)["ref_equal"]
+
+
+def test_host_narrowing_is_exact_and_reports_values_outside_a_byte():
+    """dvs_host_narrow_i16_u8 (no GPU): every size / thread count gives the bytes NumPy's cast gives, and any value
+    outside [0, 255] -- negative ones included -- is reported."""
+    from pydvs_b200 import _lib
+    rng = np.random.default_rng(11)
+    for n, threads in ((0, 1), (1, 1), (63, 2), (64, 1), (4097, 3), (1 << 16, 4), ((1 << 18) + 37, 8), (3 * 4096 * 5, 5)):
+        src = rng.integers(0, 256, n, dtype=np.int16)
+        raw = np.zeros(n + 64, np.uint8)
+        off = (-raw.ctypes.data) % 32                    # 32-byte aligned destination: the AVX2 / streaming-store path
+        for shift in (0, 1):                             # ... and an unaligned one: the SSE2 path
+            dst = raw[off + shift:off + shift + n]
+            flag = ctypes.c_int32(7)
+            rc = _lib.lib.dvs_host_narrow_i16_u8(src.ctypes.data, dst.ctypes.data, n, threads, ctypes.byref(flag))
+            assert rc == _lib.OK and flag.value == 0
+            assert np.array_equal(dst, src.astype(np.uint8))
+    src = rng.integers(0, 256, 1 << 17, dtype=np.int16)
+    dst = np.zeros(src.size, np.uint8)
+    for pos, bad in ((0, 256), (77, -1), (src.size - 1, 300), (70000, -32768), (65536, 32767)):
+        s2 = src.copy()
+        s2[pos] = bad
+        flag = ctypes.c_int32(0)
+        assert _lib.lib.dvs_host_narrow_i16_u8(s2.ctypes.data, dst.ctypes.data, s2.size, 4, ctypes.byref(flag)) == _lib.OK
+        assert flag.value == 1, (pos, bad)
+    assert _lib.lib.dvs_host_narrow_i16_u8(None, dst.ctypes.data, 4, 1, ctypes.byref(flag)) == _lib.ERR_INVALID_ARGUMENT

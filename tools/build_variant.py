@@ -25,7 +25,7 @@ def main():
     out = os.path.join(b.HERE, "libpydvs_b200_%s.so" % name)
 
     def one(unit):
-        obj = os.path.join(obj_dir, unit.replace(".cu", ".o"))
+        obj = os.path.join(obj_dir, os.path.splitext(unit)[0] + ".o")
         r = subprocess.run([b._nvcc()] + b.NVCC_FLAGS + extra + ["-c", os.path.join(b.CSRC, unit), "-o", obj],
                            capture_output=True, text=True)
         if r.returncode:
