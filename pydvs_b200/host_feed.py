@@ -68,7 +68,7 @@ class HostFeed:
     def _calibrate(self, frames_host):
         """Seconds per frame set: host narrowing, and the plain int16 copy (measured on a slice, scaled)."""
         n = frames_host.numel()
-        m = min(n, 1 << 26)                      # up to 64 Mi pixels of the frame set
+        m = min(n, 1 << 28)                      # up to 256 Mi pixels of the frame set (small copies under-rate the link)
         src = frames_host.view(-1)[:m]
         stage = self._stage(0).view(-1)
         dev = self._dev(0, torch.int16).view(-1)
