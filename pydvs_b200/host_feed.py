@@ -87,8 +87,10 @@ class HostFeed:
             self._copy.synchronize()
             best_c = min(best_c, time.perf_counter() - t0)
         t_narrow, t_copy16 = best_n * n / m, best_c * n / m
-        # pipelined, a narrowed step costs max(narrowing, half the copy); a plain one the whole copy
-        use = max(t_narrow, 0.5 * t_copy16) < 0.95 * t_copy16
+        # pipelined, a narrowed step costs max(narrowing, half the copy) and a plain one the whole copy -- but the narrowing
+        # threads and the copy engine share the host's memory bandwidth (two ranks narrowing at once on one box: a
+        # predicted 45 against 50 ms became 52 against 47 ms), so narrowing has to win by a clear margin
+        use = max(1.25 * t_narrow, 0.5 * t_copy16) < t_copy16
         self.stats["calibration"] = {"narrow_s_per_set": t_narrow, "copy_int16_s_per_set": t_copy16, "narrow": bool(use),
                                      "threads": self.threads}
         if not use:   # give the pinned staging memory back
