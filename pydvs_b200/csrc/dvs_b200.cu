@@ -416,6 +416,9 @@ struct ExpandArgs {
 // NS8 (n_slots <= 8, no time-binary multiplicities): every lane also pre-loads its own task's 8 segment
 // positions (coalesced over tiles) and the first records of the NEXT task are prefetched while the
 // current one is expanded, so the dependent-load chain per task is off the critical path.
+#ifndef EXPAND_SMALL_TASK
+#define EXPAND_SMALL_TASK 4
+#endif
 #ifndef EXPAND_MINB
 #define EXPAND_MINB 5   // 48 registers (no spills on the NS8 path); 4 / 6 / 8 measured within 5 us of each other at 256 x 4K
 #endif
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(256, EXPAND_MINB) k_expand(const __grid_consta
     }
     // Tasks with a handful of records (the usual case on sparse frames: one or two per tile) are expanded by
     // their own lane, 32 tasks at a time, instead of occupying the whole warp one after the other.
-    constexpr int kSmallTask = 4;
+    constexpr int kSmallTask = EXPAND_SMALL_TASK;
     if (__any_sync(kFull, my_n > 0 && my_n <= kSmallTask)) {
       if (my_n > 0 && my_n <= kSmallTask) {
         const uint32_t pb = (my_pol ? 0xffffu : 1u) << 16;

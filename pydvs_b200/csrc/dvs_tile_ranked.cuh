@@ -49,8 +49,8 @@ namespace dvs {
 #define FAST2R_MINB_512 4
 #endif
 #ifndef RANKED_QUIET_SKIP
-#define RANKED_QUIET_SKIP 0   // one early-out per 2 x 8 block ahead of the per-area loop: the flag pass keeps its differences
-                              // alive (60 B of spills at 48 registers), K1 at 64 x 4K 0.393 ms against 0.364 without
+#define RANKED_QUIET_SKIP 0   // one early-out per 2 x 8 block ahead of the per-area loop: K1 at 64 x 4K 0.405 ms against 0.336
+                              // without (packed-bytes build, 20 B of spills; eager build: 0.393 against 0.364)
 #endif
 
 template <int SRC, int JH, int ENC, int ST>
@@ -139,7 +139,7 @@ DEV void fast2r_tile(const TileArgs &A, const int t_idx, const int s_idx, unsign
       uint32_t any = 0u;
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
-        const uint32_t cu = c_pk[ju][w], ru = r_pk[ju][w], cl = c_pk[jl][w], rl = r_pk[jl][w];
+        const uint32_t cu = c_word(ju, w), ru = r_word(ju, w), cl = c_word(jl, w), rl = r_word(jl, w);
         any |= ((__vmaxu2(cu, ru) - __vminu2(cu, ru)) + kadd) | ((__vmaxu2(cl, rl) - __vminu2(cl, rl)) + kadd);
       }
       if ((any & 0x80008000u) == 0u) continue;
