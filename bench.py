@@ -46,6 +46,8 @@ WORKLOADS = {
                                   num_bins=None, hw=1.0, ref0=128),
     "4k_rate_inhibition_4x4": dict(W=3840, H=2160, S=256, output_type="RATE", inh=4, adaptive=False, max_time_ms=8,
                                    num_bins=None, hw=1.0, ref0=128),
+    "davis346_rate_inhibition": dict(W=346, H=260, S=1024, output_type="RATE", inh=2, adaptive=False, max_time_ms=8,
+                                     num_bins=None, hw=1.0, ref0=128),
     "davis346_rate": dict(W=346, H=260, S=1024, output_type="RATE", inh=0, adaptive=False, max_time_ms=8, num_bins=None,
                           hw=1.0, ref0=128),
     "1080p_time_adaptive": dict(W=1920, H=1080, S=64, output_type="TIME", inh=0, adaptive=True, max_time_ms=4,
@@ -70,6 +72,8 @@ SUITE = [
     ("cfg2_mnist_shape_4096_streams_time_bin_thr_adaptive", dict(workload="mnist_time_bin_thr_adaptive", settle=4)),
     ("cfg3_vga_rate_inhibition", dict(workload="vga_rate_inhibition")),
     ("cfg1_128_rate", dict(workload="128_rate", settle=4)),
+    # a real sensor shape whose rows are not a multiple of 8 pixels, with inhibition: planes kept with padded rows
+    ("davis346_rate_inhibition_1024_streams", dict(workload="davis346_rate_inhibition")),
 ]
 
 

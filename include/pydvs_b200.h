@@ -258,6 +258,11 @@ int dvs_gather_split(int32_t s, int32_t tiles_per_stream, int32_t tile_px, int32
                      int16_t *pos_out, int64_t pos_stride, int16_t *neg_out, int64_t neg_stride,
                      void *stream);
 
+/* Frame rows of W pixels -> rows of Wp pixels (Wp = W rounded up to a multiple of 8, pad columns zero): lets a caller
+ * keep its planes with 16-byte aligned rows, so that geometries such as 346 x 260 (DAVIS346) with local_inhibition
+ * (gs:177-221) run the register-only tile kernels; pad pixels (frame 0, reference 0) never exceed a threshold >= 0. */
+int dvs_pad_rows(const void *src, void *dst, int64_t rows, int32_t W, int32_t Wp, int32_t elem_bytes, void *stream);
+
 /* The reference's 16-bit AER key for each event: coded spike_to_key gs:744-778 (uncoded = 0) or
  * gsu:676-705 (uncoded = 1), including the truncation to uint16 and the int16 return type. */
 int dvs_keys_from_events(const dvs_event *events, int64_t n, int32_t uncoded, int32_t flag_shift,

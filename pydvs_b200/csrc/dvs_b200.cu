@@ -649,6 +649,26 @@ __global__ void __launch_bounds__(256, EXPAND_MINB) k_expand(const __grid_consta
 }
 
 // ================================================================================================
+// rows of W pixels -> rows of Wp pixels (Wp % 8 == 0, pad columns zero): the frame copy in front of the tile pass
+// when the planes are kept with padded rows (DVSStreams, rows that are not a multiple of 8 pixels with inhibition).
+// One thread per 8 destination pixels, four pair loads (W is even: every row starts on a pair boundary).
+// ================================================================================================
+template <typename PAIR, typename VEC>
+__global__ void __launch_bounds__(256) k_pad_rows(const PAIR *__restrict__ src, VEC *__restrict__ dst, long long n_groups,
+                                                  int pairs_per_row, int groups_per_row) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_groups) return;
+  const long long r = i / groups_per_row;
+  const int g = (int)(i - r * groups_per_row);
+  const PAIR *s = src + r * pairs_per_row + g * 4;
+  uint32_t v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = g * 4 + k < pairs_per_row ? (uint32_t)s[k] : 0u;
+  if constexpr (sizeof(PAIR) == 4) dst[i] = make_uint4(v[0], v[1], v[2], v[3]);
+  else dst[i] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+}
+
+// ================================================================================================
 // gather tile-local record lists of one stream into contiguous (rows; cols; vals) arrays
 // ================================================================================================
 __global__ void __launch_bounds__(256) k_gather_split(int s, int tps, int tile_px, int C,
@@ -1405,6 +1425,23 @@ int dvs_move_mask_i16(const int16_t *images, int32_t n_images, const int32_t *im
   k_move_mask<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(images, n_images, img_index, dx, dy, bg, mask, out,
                                                                        S, H, W);
   return check_launch("k_move_mask");
+}
+
+int dvs_pad_rows(const void *src, void *dst, int64_t rows, int32_t W, int32_t Wp, int32_t elem_bytes, void *stream) {
+  if (!src || !dst || rows < 0 || W <= 0 || (W & 1) || Wp < W || Wp - W >= 8 || (Wp & 7) || (elem_bytes != 1 && elem_bytes != 2))
+    return fail(DVS_ERR_INVALID_ARGUMENT, "pad_rows: W even, Wp = W rounded up to a multiple of 8, 1- or 2-byte pixels");
+  if ((reinterpret_cast<uintptr_t>(src) & (2 * elem_bytes - 1)) || (reinterpret_cast<uintptr_t>(dst) & (8 * elem_bytes - 1)))
+    return fail(DVS_ERR_INVALID_ARGUMENT, "pad_rows: unaligned buffer");
+  const long long n_groups = (long long)rows * (Wp / 8);
+  if (n_groups == 0) return DVS_OK;
+  const unsigned grid = (unsigned)((n_groups + 255) / 256);
+  if (elem_bytes == 2)
+    k_pad_rows<uint32_t, uint4><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint32_t *>(src), static_cast<uint4 *>(dst),
+                                                                  n_groups, W / 2, Wp / 8);
+  else
+    k_pad_rows<uint16_t, uint2><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint16_t *>(src), static_cast<uint2 *>(dst),
+                                                                  n_groups, W / 2, Wp / 8);
+  return check_launch("k_pad_rows");
 }
 
 int dvs_keys_from_events(const dvs_event *events, int64_t n, int32_t uncoded, int32_t flag_shift, int32_t data_shift,

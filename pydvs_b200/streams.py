@@ -183,20 +183,29 @@ class DVSStreams:
         self.inh_k = k
         if k > 1 and (self.W % k or self.H % k):
             raise IndexError("local inhibition needs width and height divisible by inh_area_width")
+        # Row pitch of the resident planes.  The register-only inhibition kernels need rows that start on 16-byte
+        # boundaries (W % 8 == 0); a sensor such as the DAVIS346 (346 x 260) with 2x2 inhibition would otherwise take the
+        # generic body at a twentieth of the speed.  The state planes are ours, so they are kept with rows padded to a
+        # multiple of 8 pixels and every frame is copied into a padded buffer first (one extra pass over the frame):
+        # pad pixels hold 0 in frame and reference, never exceed a threshold >= 0, never spike, never reach an event.
+        t0_ = cfg.threshold if cfg.threshold0 is None else cfg.threshold0
+        pad_ok = (k in (2, 4) and self.W % 8 != 0 and not debug_planes and not force_generic and cfg.tile_rows is None
+                  and int(cfg.threshold) >= 0 and (not cfg.adaptive_threshold or (int(cfg.min_threshold) >= 0 and int(t0_) >= 0)))
+        self.Wp = (self.W + 7) // 8 * 8 if pad_ok else self.W
         self.enc_mode = _ENC[cfg.output_type]
         self.upd_mode = _lib.UPD_RATE_ADPT if cfg.adaptive_threshold else _UPD[cfg.output_type]
         self.n_slots = cfg.max_time_ms if cfg.output_type == OUTPUT_RATE else cfg.num_bins
         if cfg.encoder_threshold == 0 and self.enc_mode != _lib.ENC_TIME_BIN:
             raise ZeroDivisionError("integer division or modulo by zero")
         with torch.cuda.device(self.device):
-            tr = cfg.tile_rows or lib.dvs_choose_tile_rows(self.S, self.H, self.W, k)
+            tr = cfg.tile_rows or lib.dvs_choose_tile_rows(self.S, self.H, self.Wp, k)
         if tr <= 0:
             raise NotImplementedError("frame too wide for one tile (width * inh_area_width > 32768)")
         self.tile_rows = tr
         self.tps = (self.H + tr - 1) // tr
-        self.tile_px = tr * self.W
+        self.tile_px = tr * self.Wp
         # records reserved per tile: with k x k inhibition at most one record per area (tile_px / k^2)
-        self.rec_stride = (tr // k) * (self.W // k) if k > 1 else self.tile_px
+        self.rec_stride = (tr // k) * (self.Wp // k) if k > 1 else self.tile_px
         self.C = 2 + 2 * self.n_slots
         dev = self.device
         # state.  "int16": the planes as the reference's API holds them (``ref`` / ``thr`` ARE the resident tensors).
@@ -218,10 +227,13 @@ class DVSStreams:
                              "[0, 255] and no debug planes")
         self.state_dtype = state_dtype
         sdt = torch.uint8 if state_dtype == "uint8" else torch.int16
-        self._ref = torch.full((self.S, self.H, self.W), cfg.ref0, dtype=sdt, device=dev)
+        self._ref = torch.full((self.S, self.H, self.Wp), cfg.ref0, dtype=sdt, device=dev)
         self._thr = None
         if cfg.adaptive_threshold:
-            self._thr = torch.full((self.S, self.H, self.W), t0, dtype=sdt, device=dev)
+            self._thr = torch.full((self.S, self.H, self.Wp), t0, dtype=sdt, device=dev)
+        self._fpad = {}            # frame dtype -> padded frame buffer (rows of Wp pixels, pad columns zero)
+        if self.Wp != self.W:
+            self._ref[:, :, self.W:] = 0
         # LUT (time-binary modes)
         self.lut = None
         if self.enc_mode in (_lib.ENC_TIME_BIN, _lib.ENC_TIME_BIN_THR) or self.upd_mode in (
@@ -277,16 +289,22 @@ class DVSStreams:
         self._graph_misses = 0
 
     # state planes as int16 (the reference's dtype): the resident tensors themselves, or copies of the one-byte state
-    ref = property(lambda self: self._ref if self._ref.dtype == torch.int16 else self._ref.to(torch.int16))
-    thr = property(lambda self: None if self._thr is None else
-                   (self._thr if self._thr.dtype == torch.int16 else self._thr.to(torch.int16)))
+    # (with padded rows: the [S, H, W] part of the planes)
+    def _plane(self, t):
+        if t is None:
+            return None
+        t = t if self.Wp == self.W else t[:, :, :self.W]
+        return t if t.dtype == torch.int16 else t.to(torch.int16)
+
+    ref = property(lambda self: self._plane(self._ref))
+    thr = property(lambda self: self._plane(self._thr))
 
     def ref_plane(self, s):
         """Reference plane of stream ``s`` as int16 [H, W] (a copy when the state is held in bytes)."""
-        return self._ref[s].to(torch.int16)
+        return self._ref[s, :, :self.W].to(torch.int16)
 
     def thr_plane(self, s):
-        return None if self._thr is None else self._thr[s].to(torch.int16)
+        return None if self._thr is None else self._thr[s, :, :self.W].to(torch.int16)
 
     def set_state(self, ref=None, thr=None):
         """Overwrite the reference and / or threshold planes (int16 values; with one-byte state they must lie in
@@ -299,7 +317,7 @@ class DVSStreams:
             src = torch.as_tensor(src, device=self.device)
             if dst.dtype == torch.uint8 and src.dtype != torch.uint8 and (int(src.min()) < 0 or int(src.max()) > 255):
                 raise ValueError("%s values outside [0, 255] cannot be held in one-byte state" % name)
-            dst.copy_(src.reshape(dst.shape))
+            dst[:, :, :self.W].copy_(src.reshape(self.S, self.H, self.W))
 
     # the buffer set of the most recent step
     records = property(lambda self: self._sets[self._cur]["records"])
@@ -321,7 +339,7 @@ class DVSStreams:
 
     def _make_params(self):
         cfg, p = self.cfg, _lib.StepParams()
-        p.tiling = _lib.Tiling(self.S, self.H, self.W, self.tile_rows)
+        p.tiling = _lib.Tiling(self.S, self.H, self.Wp, self.tile_rows)
         p.frame_dtype = _lib.FRAME_U8 if cfg.frame_dtype == "uint8" else _lib.FRAME_I16
         p.adaptive, p.update_mode, p.uncoded = int(cfg.adaptive_threshold), self.upd_mode, int(cfg.uncoded)
         p.threshold, p.min_thr, p.max_thr = int(cfg.threshold), int(cfg.min_threshold), int(cfg.max_threshold)
@@ -349,7 +367,8 @@ class DVSStreams:
             raise ValueError("frames must be a CUDA tensor of dtype %s" % (ok[0],))
         if frames.numel() != self.S * self.P or not frames.is_contiguous():
             raise ValueError("frames must be contiguous with shape [%d, %d, %d]" % (self.S, self.H, self.W))
-        if self.use_graph and expand and self.frames_done > 0:   # the first step runs eagerly (module load, attributes)
+        # (the first step runs eagerly: module load, attributes, the padded frame buffer of this dtype)
+        if self.use_graph and expand and self.frames_done > 0 and (self.Wp == self.W or frames.dtype in self._fpad):
             g = self._graphs.get(frames.data_ptr())
             if g is None and len(self._graphs) < self.GRAPH_CACHE:
                 g = self._capture_step(frames)
@@ -421,6 +440,13 @@ class DVSStreams:
 
     def tile_pass(self, frames):
         """K1: fused threshold / inhibition / state update / record compaction / slot counts."""
+        if self.Wp != self.W:   # rows padded to a multiple of 8 pixels (see __init__)
+            buf = self._fpad.get(frames.dtype)
+            if buf is None:
+                buf = self._fpad[frames.dtype] = torch.zeros((self.S, self.H, self.Wp), dtype=frames.dtype, device=self.device)
+            check(lib.dvs_pad_rows(frames.data_ptr(), buf.data_ptr(), self.S * self.H, self.W, self.Wp, frames.element_size(),
+                                   current_stream_ptr()))
+            frames = buf
         self._params.curr = frames.data_ptr()
         self._params.frame_dtype = _lib.FRAME_U8 if frames.dtype == torch.uint8 else _lib.FRAME_I16
         self._params.records, self._params.tile_counts = self.records.data_ptr(), self.tile_counts.data_ptr()

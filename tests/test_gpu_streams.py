@@ -452,3 +452,44 @@ def test_random_configurations_against_the_oracle():
         except AssertionError:
             raise AssertionError("trial %d failed: S=%d H=%d W=%d %r" % (trial, S, H, W, kw))
     assert undefined <= 12, "too many draws landed in the reference's undefined region: %d" % undefined
+
+
+@pytest.mark.parametrize("state_dtype", ["int16", "uint8"])
+def test_inhibition_on_rows_that_are_not_a_multiple_of_eight_pixels_takes_the_fast_kernels(state_dtype):
+    """DAVIS346-shaped streams (346 x 260) with 2x2 / 4x4 inhibition: the planes are kept with rows padded to a multiple
+    of 8 pixels (pad pixels never spike), so the register-only kernels apply; results are those of the oracle on the
+    unpadded frames -- planes, lists, split_spikes."""
+    from pydvs_b200 import _lib
+    kw = dict(debug=False, state_dtype=state_dtype)
+    dvs = _run_case(3, 26, 346, inh=2, frames=5, source="bar", **kw)
+    assert dvs.kernel_path == _lib.PATH_FAST and dvs.Wp == 352 and tuple(dvs.ref.shape) == (3, 26, 346)
+    _run_case(2, 20, 346, inh=2, frames=4, source="random", **kw)
+    _run_case(2, 20, 346, inh=2, frames=4, source="random", frame_dtype="uint8", **kw)
+    _run_case(2, 20, 346, inh=2, frames=4, source="wide", **kw)                      # declined tiles -> generic body
+    _run_case(2, 12, 346, inh=2, frames=5, output_type="TIME", adaptive=True, num_bins=4, max_time_ms=4, thr0=12, **kw)
+    _run_case(2, 12, 346, inh=2, frames=4, hw=0.9, source="narrow", **kw)             # decay: pad pixels stay at zero
+    _run_case(2, 12, 346, inh=2, frames=4, output_type="TIME_BIN_THR", num_bins=6, source="narrow", threshold=5, **kw)
+    assert _run_case(2, 16, 348, inh=4, frames=4, source="bar", **kw).kernel_path == _lib.PATH_FAST_4X4
+    assert _run_case(1, 10, 14, inh=2, frames=4, **kw).kernel_path == _lib.PATH_FAST   # 14 -> 16 pixels per row
+    # not padded: debug planes, explicit tile rows, negative thresholds, other inhibition widths
+    assert _run_case(1, 10, 14, inh=2, frames=3).Wp == 14
+    assert _run_case(1, 12, 18, inh=3, frames=3, **kw).Wp == 18
+    from pydvs_b200 import DVSConfig, DVSStreams
+    assert DVSStreams(DVSConfig(width=14, height=10, inh_area_width=2, threshold=-1)).Wp == 14
+
+
+def test_padded_rows_under_graph_replay_and_set_state():
+    from pydvs_b200 import DVSConfig, DVSStreams, synth
+    cfg = DVSConfig(width=346, height=20, streams=2, output_type="RATE", threshold=12, inh_area_width=2)
+    eager, graphed = DVSStreams(cfg, graph=False), DVSStreams(cfg, graph=True, state_dtype="auto")
+    start = torch.randint(0, 256, (2, 20, 346), dtype=torch.int16, device="cuda")
+    eager.set_state(ref=start)
+    graphed.set_state(ref=start)
+    ring = [synth.random_frames(2, 20, 346, t, seed=8) for t in range(3)]
+    for t in range(9):
+        a, b = eager.step(ring[t % 3]), graphed.step(ring[t % 3])
+        torch.cuda.synchronize()
+        n = a.total_events()
+        assert n == b.total_events() and torch.equal(a.events_raw[:n], b.events_raw[:n])
+        assert torch.equal(eager.ref, graphed.ref)
+    assert len(graphed._graphs) == 3 and graphed.Wp == 352

@@ -1,13 +1,10 @@
-OUT=gpurun_out/s3s; mkdir -p $OUT
-PYDVS_B200_LIB=$PWD/pydvs_b200/libpydvs_b200_qskip.so python -m pytest tests/test_gpu_compact_state.py -x -q > $OUT/pytest_qskip.log 2>&1; tail -2 $OUT/pytest_qskip.log
-for LIB in main qskip; do
-  if [ "$LIB" = "main" ]; then unset PYDVS_B200_LIB; else export PYDVS_B200_LIB=$PWD/pydvs_b200/libpydvs_b200_$LIB.so; fi
-  B="--no-e2e --no-cpu-baseline --no-parity --configs none --steps 20 --warmup 3 --ring 8"
-  for W in "--streams 256" "--streams 64" "--streams 64 --pattern dense --settle 2" "--streams 64 --frame-dtype uint8" "--workload vga_rate_inhibition --streams 2048"; do
-    python bench.py $B $W 2>/dev/null | python -c "
-import sys, json
-d = json.loads(sys.stdin.read().strip().splitlines()[-1]); r = d['roofline']
-print(json.dumps({'lib': '$LIB', 'args': '$W', 'ms': round(d['ms_per_step'], 4), 'k1_ms': round(r['k1_ms'], 4), 'events': d['details']['events_last_step']}))" >> $OUT/sweep.jsonl
-  done
-done
-cat $OUT/sweep.jsonl
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo rc=$? >> gpurun_out/pytest.log; tail -12 gpurun_out/pytest.log
+OUT=gpurun_out/s3t; mkdir -p $OUT
+B="--no-e2e --no-cpu-baseline --configs none --steps 20 --warmup 3 --ring 8"
+python bench.py $B --workload davis346_rate_inhibition > $OUT/davis_inh.json 2>$OUT/davis_inh.err; tail -c 300 $OUT/davis_inh.err
+python bench.py $B --workload davis346_rate_inhibition --k1-variant generic > $OUT/davis_inh_generic.json 2>$OUT/davis_inh_generic.err
+python bench.py $B --workload davis346_rate > $OUT/davis.json 2>$OUT/davis.err
+for f in davis_inh davis_inh_generic davis; do python -c "
+import json
+d=json.loads(open('$OUT/$f.json').read().strip().splitlines()[-1]); r=d['roofline']
+print('$f', d['ms_per_step'], r['k1_ms'], r['frac'], d['details']['events_last_step'], d.get('parity_check',{}).get('all_configs_equal'))"; done
