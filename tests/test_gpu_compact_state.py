@@ -95,3 +95,35 @@ def test_state_dtype_selection_and_accessors():
     with pytest.raises(ValueError):
         auto.set_state(ref=start + 1000)
     assert auto.thr_plane(0) is None
+
+
+def test_byte_state_under_capture_replay_pipelined_expand_and_padded_rows():
+    from pydvs_b200 import DVSConfig, DVSStreams, synth
+    # capture() / replay() on byte state: the warm-up snapshot restores the byte planes
+    cfg = DVSConfig(width=128, height=128, streams=1, output_type="RATE", inh_area_width=2)
+    eager, graphed = DVSStreams(cfg, graph=False), DVSStreams(cfg, graph=False, state_dtype="uint8")
+    static = synth.moving_bar(1, 128, 128, 0, noise=6, seed=1)
+    graphed.capture(static)
+    assert graphed.frames_done == 0 and int((graphed.ref != 128).sum()) == 0
+    for t in range(6):
+        f = synth.moving_bar(1, 128, 128, t, noise=6, seed=1)
+        re = eager.step(f)
+        static.copy_(f)
+        rg = graphed.replay()
+        assert torch.equal(eager.ref, graphed.ref)
+        assert torch.equal(re.seg_offsets, rg.seg_offsets) and torch.equal(re.events(), rg.events())
+    # expand on the side stream (pipeline_depth 2), rows padded to a multiple of 8 pixels, uint8 frames handed to an
+    # int16 configuration: all at once against the plain int16-state object
+    cfg = DVSConfig(width=346, height=20, streams=3, output_type="TIME", num_bins=8, max_time_ms=8, inh_area_width=2)
+    plain = DVSStreams(cfg, graph=False, event_capacity=3 * 20 * 346)
+    piped = DVSStreams(cfg, state_dtype="uint8", pipeline_depth=2, event_capacity=3 * 20 * 346)
+    assert piped.Wp == 352 and plain.Wp == 352
+    for t in range(7):
+        f = synth.random_frames(3, 20, 346, t, seed=5)
+        a = plain.step(f)
+        b = piped.step(f.to(torch.uint8) if t % 2 else f)
+        piped.drain()
+        torch.cuda.synchronize()
+        n = a.total_events()
+        assert n == b.total_events() and torch.equal(a.events_raw[:n], b.events_raw[:n])
+        assert torch.equal(plain.ref, piped.ref)
