@@ -81,6 +81,13 @@ def test_choose_tile_rows_and_argument_errors_without_a_gpu():
     assert b"null" in lib.dvs_last_error_string()
     assert lib.dvs_local_inhibition_i16(ctypes.c_void_p(16), ctypes.c_void_p(16), 1, 6, 10, 4, None) == _lib.ERR_INVALID_ARGUMENT
     assert lib.dvs_scan_tiles(0, 1, 1, None, None, None, None, None) == _lib.ERR_INVALID_ARGUMENT
+    # dvs_pad_rows: W even, Wp = W rounded up to a multiple of 8, 1- or 2-byte pixels, aligned buffers
+    P = ctypes.c_void_p
+    for args in ((P(64), P(64), 4, 345, 352, 2), (P(64), P(64), 4, 346, 360, 2), (P(64), P(64), 4, 346, 350, 2),
+                 (P(64), P(64), 4, 346, 352, 4), (P(66), P(64), 4, 346, 352, 2), (P(64), P(72), 4, 346, 352, 2),
+                 (None, P(64), 4, 346, 352, 2)):
+        assert lib.dvs_pad_rows(*args, None) == _lib.ERR_INVALID_ARGUMENT, args
+    assert lib.dvs_pad_rows(P(64), P(64), 0, 346, 352, 2, None) == _lib.OK      # nothing to do: no launch
     with pytest.raises(ValueError):
         _lib.check(_lib.ERR_INVALID_ARGUMENT)
     with pytest.raises(NotImplementedError):
