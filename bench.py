@@ -483,7 +483,12 @@ class Case:
 
     def launches_per_step(self):
         d = self.dvs
-        return 2 + (1 if d.S * 2 * d.n_slots <= 8192 else 4) + 1   # K1, redo, scan (+ segment scans when many), expand
+        # K1 (+ dvs_pad_rows in front of it when the planes are kept with padded rows), redo, scan, expand.  The scan is one
+        # launch (the last CTA builds the row pointers, dvs_scan_tiles_ticket) up to 8192 (stream, slot, polarity) segments;
+        # beyond that: k_scan_small + k_seg_fill for streams of at most 8 tiles, else the tile scan + three segment launches
+        small = d.S * 2 * d.n_slots <= 8192
+        scan = 1 if small else (2 if d.tps <= 8 else 4)
+        return (1 if d.Wp != d.W else 0) + 2 + scan + 1
 
     def timed(self, K, warmup, barrier, sampler=None, split=True):
         """K steps bracketed by CUDA events on the launching stream.  split: per-launch events around K1."""
