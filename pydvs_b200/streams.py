@@ -174,7 +174,7 @@ class DVSStreams:
 
     def __init__(self, cfg: DVSConfig, device=None, event_capacity: Optional[int] = None,
                  debug_planes: bool = False, force_generic: bool = False, pipeline_depth: int = 1,
-                 split_lists: bool = True, graph="auto", state_dtype: str = "int16"):
+                 split_lists: bool = True, graph="auto", state_dtype: str = "auto"):
         if not torch.cuda.is_available():
             raise RuntimeError("pydvs_b200 needs a CUDA device (there is no CPU path)")
         self.cfg = cfg = cfg.resolved()
@@ -213,8 +213,9 @@ class DVSStreams:
         # state.  "int16": the planes as the reference's API holds them (``ref`` / ``thr`` ARE the resident tensors).
         # "uint8": one byte per pixel -- every update rule clips the reference to [0, 255] (gs:251, 297, 378, 425) and
         # the coded threshold rule to [min, max] (gs:297), so for a start inside [0, 255] the bytes hold the reference's
-        # own values and a step moves half the state bytes (``ref`` / ``thr`` then return int16 COPIES; write with
-        # set_state()).  "auto": uint8 whenever that is exact for this configuration.
+        # own values and a step moves half the state bytes (``ref`` / ``thr`` then return int16 COPIES: read them
+        # freely, write with set_state()).  "auto" (the default): uint8 whenever that is exact for this configuration,
+        # int16 otherwise (ref0 / thresholds outside a byte, the uncoded threshold rule, debug planes).
         t0 = cfg.threshold if cfg.threshold0 is None else cfg.threshold0
         compact_ok = (0 <= int(cfg.ref0) <= 255 and not debug_planes and
                       (not cfg.adaptive_threshold or

@@ -73,7 +73,7 @@ def test_state_dtype_selection_and_accessors():
     cfg = DVSConfig(width=64, height=16, streams=2, output_type="RATE", threshold=12, inh_area_width=2)
     auto = DVSStreams(cfg, state_dtype="auto")
     assert auto.state_dtype == "uint8" and auto.ref.dtype == torch.int16 and auto.thr is None
-    assert DVSStreams(cfg).state_dtype == "int16"                       # the default stays the reference's layout
+    assert DVSStreams(cfg).state_dtype == "uint8"                       # the default: bytes wherever that is exact
     assert DVSStreams(DVSConfig(width=64, height=16, streams=1, ref0=300), state_dtype="auto").state_dtype == "int16"
     assert DVSStreams(cfg, state_dtype="auto", debug_planes=True).state_dtype == "int16"
     unc = DVSConfig(width=64, height=16, streams=1, adaptive_threshold=True, uncoded=True)
@@ -83,7 +83,8 @@ def test_state_dtype_selection_and_accessors():
     with pytest.raises(ValueError):
         DVSStreams(DVSConfig(width=64, height=16, streams=1, ref0=-1), state_dtype="uint8")
     # both layouts walk the same states; set_state() writes either of them
-    wide = DVSStreams(cfg)
+    wide = DVSStreams(cfg, state_dtype="int16")
+    assert wide.ref.data_ptr() == wide._ref.data_ptr()                  # int16 state: `ref` IS the resident tensor
     start = torch.randint(0, 256, (2, 16, 64), dtype=torch.int16, device="cuda")
     auto.set_state(ref=start)
     wide.set_state(ref=start)
