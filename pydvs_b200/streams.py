@@ -392,6 +392,8 @@ class DVSStreams:
     def _capture_step(self, frames):
         """Record the launches of one step reading the buffer at ``frames.data_ptr()`` into a CUDA graph.  The graph is
         only replayed for a validated frames tensor at that same address, so no reference to ``frames`` is kept."""
+        if self.Wp != self.W and frames.dtype not in self._fpad:   # (allocated outside the capture)
+            self._fpad[frames.dtype] = torch.zeros((self.S, self.H, self.Wp), dtype=frames.dtype, device=self.device)
         graph = torch.cuda.CUDAGraph()
         self._cur = 0
         with torch.cuda.graph(graph):
