@@ -676,6 +676,7 @@ def run_suite_entry(args, name, ov, device, barrier, headline_case, peak):
              "cuda_graph": bool(case.dvs.use_graph), "launches_per_step": case.launches_per_step(),
              "events_last_step": t["events_last_step"], "tile_rows": case.dvs.tile_rows, "state_dtype": sdt,
              "layout_bytes_per_px": layout_bytes_per_px(wl, fdt, sdt),
+             "frac_of_layout_bytes": layout_bytes_per_px(wl, fdt, sdt) * S * case.P / (k1_ms / 1e3) / 1e9 / peak,
              # (bytes/px * pixels + 8 * events) / time -- K1 writes one 8-byte record per spike
              "frac_with_events": (k1_bytes + 8 * t["events_last_step"]) / (k1_ms / 1e3) / 1e9 / peak}
     if l2_resident:
@@ -992,6 +993,8 @@ def run_ours(args, wl, rank, local_rank, world):
                      "state_dtype": dvs.state_dtype,
                      "layout_bytes_per_px": layout_bytes_per_px(wl, args.frame_dtype, dvs.state_dtype),
                      "frac_with_events": (k1_bytes + 8 * events_last_step) / (k1_ms / 1e3) / 1e9 / peak,
+                     # the same fraction on the compulsory bytes of the layout actually resident (byte state: 2 + 1 + 1 B/px)
+                     "frac_of_layout_bytes": layout_bytes_per_px(wl, args.frame_dtype, dvs.state_dtype) * S * P / (k1_ms / 1e3) / 1e9 / peak,
                      "scan_expand_ms": rest_ms, "k1_share_of_step": (k1_ms / (k1_ms + rest_ms)) if rest_ms else None,
                      "step_achieved_gbs": step_bytes / (elapsed_ms / K / 1e3) / 1e9,
                      "traffic_gbs": (traffic / (k1_ms / 1e3) / 1e9) if traffic else None,
