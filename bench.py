@@ -753,9 +753,9 @@ def run_pipeline_entry(args, device, peak):
 
     def one(keep, sink):
         ok, batch = cam.read()
-        if keep:
+        if keep:   # (kept on the device: a download here would synchronise every frame; converted after the timing)
             for s in frames_host:
-                frames_host[s].append(batch[s].cpu().numpy())
+                frames_host[s].append(batch[s].clone())
         res = dvs.step(batch)
         if sink:
             return res.offsets_host(), res.keys(fs, ds, dm).cpu().numpy()
@@ -773,6 +773,7 @@ def run_pipeline_entry(args, device, peak):
         torch.cuda.synchronize()
         out[sink] = (time.perf_counter() - t0) / K
     dvs.check_status()
+    frames_host = {s: [f.cpu().numpy() for f in frs] for s, frs in frames_host.items()}
     entry = {"workload": "mnist_virtualcam_pipeline", "width": W, "height": H, "streams": S, "coding": "TIME_BIN_THR",
              "adaptive_threshold": True, "source": "VirtualCam SACCADE + fade mask on the reference's mnist/t10k fixtures",
              "steps": K, "ms_per_step": out[False] * 1e3, "stream_frames_per_s": S / out[False],
