@@ -6,6 +6,7 @@
 // hides everything else), so the feed narrows them to bytes on the host cores -- exactly, every value is checked -- and
 // the fused step reads them through its uint8 frame path (DVS_FRAME_U8), which produces identical results for values
 // in [0, 255].  A frame with a value outside that range is reported and the caller copies the int16 plane instead.
+#include <atomic>
 #include <cstdint>
 #include <thread>
 #include <vector>
@@ -73,13 +74,24 @@ extern "C" int dvs_host_narrow_i16_u8(const int16_t *src, uint8_t *dst, int64_t 
   int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
   if (nt < 1) nt = 1;
   if (nt > 256) nt = 256;
-  // chunks of whole 4 KB pages of the destination, so that two threads never share a cache line / streaming buffer
-  const int64_t chunk = ((n + nt - 1) / nt + 4095) / 4096 * 4096;
+  // Work is handed out in 1 MiB-of-destination pieces through an atomic counter rather than one static slice per thread:
+  // the feed's threads share the cores with the caller's own threads (a stream-synchronising main thread spins), and a
+  // static split makes the whole call wait for the one slice that lost its core.  Pieces are whole pages of the
+  // destination, so two threads never share a cache line / streaming buffer.
+  const int64_t piece = 1 << 20;
+  const int64_t n_pieces = (n + piece - 1) / piece;
+  if (nt > n_pieces) nt = (int)(n_pieces > 0 ? n_pieces : 1);
   std::vector<uint32_t> bits((size_t)nt, 0u);
+  std::atomic<int64_t> next(0);
   auto work = [&](int t) {
-    const int64_t lo = (int64_t)t * chunk, hi = lo + chunk < n ? lo + chunk : n;
-    if (lo >= hi) return;
-    bits[(size_t)t] = avx2 ? narrow_avx2(src + lo, dst + lo, hi - lo) : narrow_sse2(src + lo, dst + lo, hi - lo);
+    uint32_t acc = 0;
+    for (;;) {
+      const int64_t k = next.fetch_add(1, std::memory_order_relaxed);
+      if (k >= n_pieces) break;
+      const int64_t lo = k * piece, hi = lo + piece < n ? lo + piece : n;
+      acc |= avx2 ? narrow_avx2(src + lo, dst + lo, hi - lo) : narrow_sse2(src + lo, dst + lo, hi - lo);
+    }
+    bits[(size_t)t] = acc;
   };
   if (nt == 1 || n < (1 << 16)) {
     for (int t = 0; t < nt; ++t) work(t);

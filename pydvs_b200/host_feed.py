@@ -9,8 +9,10 @@ by the PCIe copy of those planes (bench.py's e2e leg moves them at 0.98 of the p
   every value checked), copies half the bytes and lets the fused step read them through its uint8 frame path -- the
   results are identical for values in [0, 255]; a frame set with any other value is copied as int16 instead.
 
-``narrow="auto"`` times both ways on the first frame set (all ranks of a job do so at the same time, so a host that is
-short of cores or memory bandwidth is seen) and keeps the faster one.
+``narrow="auto"`` decides on the job's own first frame sets: sets 0-2 are narrowed, sets 3-4 copied as they are, and
+the feed compares what a steady-state step costs either way -- max(host narrowing time, duration of the byte copy that ran
+beside it) against the duration of the int16 copy, both taken under the real contention for the host's memory (all
+ranks of a job walk through the same phases together) -- and keeps the faster way from set 5 on.
 """
 import ctypes as C
 import os
@@ -37,6 +39,7 @@ class HostFeed:
         self._step_done = [None, None]    # event: the step that read device slot i has finished
         self._pool = ThreadPoolExecutor(max_workers=1)
         self._n = 0
+        self._trial = None
         self._outstanding = 0
         self.stats = {"narrowed": 0, "plain": 0, "out_of_range": 0, "narrow_seconds": 0.0, "calibration": None}
         if narrow is True or narrow == "auto":
@@ -65,34 +68,21 @@ class HostFeed:
         self.stats["narrow_seconds"] += time.perf_counter() - t0
         return flag.value == 0
 
-    def _calibrate(self, frames_host):
-        """Seconds per frame set: host narrowing, and the plain int16 copy (measured on a slice, scaled)."""
-        n = frames_host.numel()
-        m = min(n, 1 << 28)                      # up to 256 Mi pixels of the frame set (small copies under-rate the link)
-        src = frames_host.view(-1)[:m]
-        stage = self._stage(0).view(-1)
-        dev = self._dev(0, torch.int16).view(-1)
-        flag = C.c_int32(0)
-        best_n = best_c = 1e9
-        with torch.cuda.stream(self._copy):      # (first touch of the device buffer, outside the timing)
-            dev[:m].copy_(src, non_blocking=True)
-        for _ in range(2):
-            t0 = time.perf_counter()
-            check(lib.dvs_host_narrow_i16_u8(C.c_void_p(src.data_ptr()), C.c_void_p(stage.data_ptr()), m, self.threads, C.byref(flag)))
-            best_n = min(best_n, time.perf_counter() - t0)
-            torch.cuda.synchronize(self.device)
-            t0 = time.perf_counter()
-            with torch.cuda.stream(self._copy):
-                dev[:m].copy_(src, non_blocking=True)
-            self._copy.synchronize()
-            best_c = min(best_c, time.perf_counter() - t0)
-        t_narrow, t_copy16 = best_n * n / m, best_c * n / m
-        # pipelined, a narrowed step costs max(narrowing, half the copy) and a plain one the whole copy -- but the narrowing
-        # threads and the copy engine share the host's memory bandwidth (two ranks narrowing at once on one box: a
-        # predicted 45 against 50 ms became 52 against 47 ms), so narrowing has to win by a clear margin
-        use = max(1.25 * t_narrow, 0.5 * t_copy16) < t_copy16
-        self.stats["calibration"] = {"narrow_s_per_set": t_narrow, "copy_int16_s_per_set": t_copy16, "narrow": bool(use),
-                                     "threads": self.threads}
+    AUTO_NARROWED, AUTO_SETS = 3, 5          # "auto": sets 0-2 narrowed, sets 3-4 plain, decision before set 5
+
+    def _decide(self):
+        """narrow="auto": steady-state cost of a step either way, from the first AUTO_SETS frame sets."""
+        tr = self._trial
+        tr["ev"][1][1].synchronize()
+        tr["ev"][self.AUTO_SETS - 1][1].synchronize()
+        t_narrow = tr["narrow_s"][2]                                       # ran while the bytes of set 1 were on the wire
+        t_copy8 = tr["ev"][1][0].elapsed_time(tr["ev"][1][1]) / 1e3        # ... and this is that copy
+        t_copy16 = tr["ev"][self.AUTO_SETS - 1][0].elapsed_time(tr["ev"][self.AUTO_SETS - 1][1]) / 1e3
+        # (a narrowed step is bound by the slower of the two; 5 % for the bubbles of the three-stage pipeline)
+        use = 1.05 * max(t_narrow, t_copy8) < t_copy16
+        self.stats["calibration"] = {"narrow_s_per_set": t_narrow, "copy_bytes_s_per_set": t_copy8,
+                                     "copy_int16_s_per_set": t_copy16, "narrow": bool(use), "threads": self.threads}
+        self._trial = None
         if not use:   # give the pinned staging memory back
             self._stage8 = [None, None]
             self._dev8 = [None, None]
@@ -102,28 +92,45 @@ class HostFeed:
         """Worker thread: (narrow ->) enqueue the H2D copy of one frame set; returns (device tensor, copy-done event)."""
         if self.device.index is not None:
             torch.cuda.set_device(self.device)
+        trial = None
         if self.narrow == "auto" and frames_host.dtype == torch.int16:
-            self.narrow = self._calibrate(frames_host)
-        want_narrow = self.narrow is True and frames_host.dtype == torch.int16
+            if self._trial is None:
+                self._trial = {"k": 0, "narrow_s": {}, "ev": {}}
+            trial = self._trial["k"]
+            self._trial["k"] += 1
+            if trial >= self.AUTO_SETS:
+                self.narrow, trial = self._decide(), None
+        want_narrow = frames_host.dtype == torch.int16 and (self.narrow is True or (trial is not None and trial < self.AUTO_NARROWED))
         src, dtype = frames_host, frames_host.dtype
         if want_narrow:
             if self._h2d_done[slot] is not None:
                 self._h2d_done[slot].synchronize()       # the copy that last read this staging buffer
             stage = self._stage(slot)
-            if self._narrow_into(frames_host, stage):
+            t0 = time.perf_counter()
+            ok = self._narrow_into(frames_host, stage)
+            if trial is not None:
+                self._trial["narrow_s"][trial] = time.perf_counter() - t0
+            if ok:
                 src, dtype = stage, torch.uint8
                 self.stats["narrowed"] += 1
             else:
                 self.stats["out_of_range"] += 1
+                if trial is not None:   # "auto": frames that do not fit a byte make the question moot
+                    self.narrow, self._trial, trial = False, None, None
         if src is frames_host:
             self.stats["plain"] += 1
         dev = self._dev(slot, dtype)
         with torch.cuda.stream(self._copy):
             if self._step_done[slot] is not None:
                 self._copy.wait_event(self._step_done[slot])   # the step that last read this device buffer
+            if trial is not None:
+                began = torch.cuda.Event(enable_timing=True)
+                began.record(self._copy)
             dev.copy_(src, non_blocking=True)
-            done = torch.cuda.Event()
+            done = torch.cuda.Event(enable_timing=trial is not None)
             done.record(self._copy)
+            if trial is not None:
+                self._trial["ev"][trial] = (began, done)
         if src is not frames_host:
             self._h2d_done[slot] = done
         return dev, done

@@ -1,7 +1,12 @@
 # scratch command file for `gpurun -- 'bash tools/_run_tmp.sh'`
 mkdir -p gpurun_out/run
-python bench.py --steps 20 --warmup 5 --configs cfg2_pipeline_virtualcam_4096_streams,cfg2_mnist_shape_4096_streams_time_bin_thr_adaptive --no-cpu-baseline --no-e2e > gpurun_out/run/bench_p.json 2> gpurun_out/run/bench_p.err; tail -c 300 gpurun_out/run/bench_p.err
+python bench.py --steps 20 --warmup 5 --configs none --no-cpu-baseline > gpurun_out/run/bench_e.json 2> gpurun_out/run/bench_e.err; tail -c 300 gpurun_out/run/bench_e.err
 python -c "
 import json
-d=json.loads(open('gpurun_out/run/bench_p.json').read().strip().splitlines()[-1])
-for k,v in d['configs'].items(): print(k, {a:b for a,b in v.items() if a in ('ms_per_step','stream_frames_per_s','ms_per_step_with_sink','stream_frames_per_s_with_sink','parity','error')})"
+d=json.loads(open('gpurun_out/run/bench_e.json').read().strip().splitlines()[-1]); e=d['e2e']
+print(e['value'], e['plain_int16_copy']['value'], e['uint8_host_frames']['value'], e['host_narrowing'])"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 --no-parity --no-weak-leg > gpurun_out/run/bench_e2.json 2> gpurun_out/run/bench_e2.err; tail -c 300 gpurun_out/run/bench_e2.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/run/bench_e2.json').read().strip().splitlines()[-1]); e=d['e2e']
+print(d['value'], e['value'], e['plain_int16_copy']['value'], e['uint8_host_frames']['value'], e['host_narrowing'], e['h2d_peak_gbs'])"
