@@ -267,6 +267,10 @@ int dvs_pad_rows(const void *src, void *dst, int64_t rows, int32_t W, int32_t Wp
  * gsu:676-705 (uncoded = 1), including the truncation to uint16 and the int16 return type. */
 int dvs_keys_from_events(const dvs_event *events, int64_t n, int32_t uncoded, int32_t flag_shift,
                          int32_t data_shift, int32_t data_mask, int16_t *keys, void *stream);
+/* The same with the number of events read on the device (`n_dev`: e.g. the last CSR row pointer of the step, clamped to
+ * `cap`): a sink can queue the key pass and its copies behind a step without a host round trip for the count. */
+int dvs_keys_from_events_devn(const dvs_event *events, const int64_t *n_dev, int64_t cap, int32_t uncoded,
+                              int32_t flag_shift, int32_t data_shift, int32_t data_mask, int16_t *keys, void *stream);
 
 /* ---- frame sources (the step before the hot path) ----------------- */
 

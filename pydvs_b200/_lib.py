@@ -101,6 +101,7 @@ _SIGNATURES = {
     "dvs_gather_split": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _I64, _P, _I64, _P]),
     "dvs_keys_from_events": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P]),
     "dvs_pad_rows": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _P]),
+    "dvs_keys_from_events_devn": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P]),
     "dvs_move_mask_i16": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _P, _P, _I32, _I32, _I32, _P]),
     "dvs_attention_targets_i16": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P]),
     "dvs_animate_i16": (C.c_int, [_I32, _P, _I32, _P, _P, _D, _I32, _I32, _P, _I32, _I32, _I32, _P]),

@@ -939,6 +939,20 @@ __global__ void __launch_bounds__(256) k_keys_from_events(const dvs_event *__res
   keys[i] = (int16_t)spike_key(y, x, p > 0, uncoded, flag_shift, data_shift, data_mask);
 }
 
+// the same with the event count read on the DEVICE (the last CSR row pointer of the step), so that a sink can queue the
+// key pass behind a step without the host ever learning the count first
+__global__ void __launch_bounds__(256) k_keys_from_events_devn(const dvs_event *__restrict__ ev, const long long *__restrict__ n_dev,
+                                                               long long cap, int uncoded, int flag_shift, int data_shift,
+                                                               int data_mask, int16_t *__restrict__ keys) {
+  const long long n = min(*n_dev, cap);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {   // (the grid is sized by the SMs)
+    const uint2 e = *reinterpret_cast<const uint2 *>(ev + i);
+    const int x = e.x & 0xffff, y = e.x >> 16, p = (short)(e.y >> 16);
+    keys[i] = (int16_t)spike_key(y, x, p > 0, uncoded, flag_shift, data_shift, data_mask);
+  }
+}
+
 // batched move_image (+ mask_image): one thread per output pixel, gs:1184-1215 / gs:1124-1127
 __global__ void __launch_bounds__(256) k_move_mask(const int16_t *__restrict__ images, int n_images,
                                                    const int32_t *__restrict__ img_index, const int32_t *__restrict__ dx,
@@ -1451,6 +1465,16 @@ int dvs_keys_from_events(const dvs_event *events, int64_t n, int32_t uncoded, in
   k_keys_from_events<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(events, n, uncoded, flag_shift, data_shift,
                                                                                 data_mask, keys);
   return check_launch("k_keys_from_events");
+}
+
+int dvs_keys_from_events_devn(const dvs_event *events, const int64_t *n_dev, int64_t cap, int32_t uncoded, int32_t flag_shift,
+                              int32_t data_shift, int32_t data_mask, int16_t *keys, void *stream) {
+  if (cap < 0 || !n_dev || (cap > 0 && (!events || !keys))) return fail(DVS_ERR_INVALID_ARGUMENT, "keys_from_events_devn arguments");
+  if (cap == 0) return DVS_OK;
+  const long long blocks = (cap + 255) / 256;
+  k_keys_from_events_devn<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, as_stream(stream)>>>(
+      events, reinterpret_cast<const long long *>(n_dev), cap, uncoded, flag_shift, data_shift, data_mask, keys);
+  return check_launch("k_keys_from_events_devn");
 }
 
 }  // extern "C"

@@ -115,3 +115,69 @@ def spike_file_lines_all_streams(result, flag_shift, data_shift, data_mask, t_fr
         lo, hi = int(bounds[s]), int(bounds[s + 1])
         out.append(["%s %f" % (int(k), t) for k, t in zip(keys[lo:hi].tolist(), times[lo:hi].tolist())])
     return out
+
+
+class AsyncKeySink:
+    """Streams the AER result of every step -- the reference's 16-bit keys (``spike_to_key``, ``generate_spikes.pyx:744-778``)
+    and the CSR row pointers of all streams -- to pinned host memory WITHOUT stalling the device pipeline.
+
+    ``push(res)`` right after ``dvs.step(...)`` queues, on the current stream, the key pass (event count read on the
+    device, ``dvs_keys_from_events_devn``) and two asynchronous copies into one of ``depth`` host slots; ``pop()`` hands
+    back the oldest slot as ``(offsets, keys)`` NumPy views once its copies have landed -- typically ``depth - 1`` steps
+    later, so the host formats / sends frame n while the device works on frame n + 1 (the reference's three-process
+    pipeline, ``external_dvs_emulator_device.py:549-683``, on streams and events).  The key copy is sized from the
+    previous steps (twice their largest count); a step that emits more is completed by a second copy in ``pop()``.
+    The views stay valid until ``depth`` further pushes.
+    """
+
+    def __init__(self, dvs, flag_shift, data_shift, data_mask, depth=2, initial_keys=1 << 16):
+        import torch
+        self.dvs, self.depth = dvs, max(1, int(depth))
+        self.params = (int(flag_shift), int(data_shift), int(data_mask))
+        self.cap = int(dvs.event_capacity)
+        dev = dvs.device
+        n_off = dvs.seg_offsets.numel()
+        self._keys_dev = [torch.empty(self.cap, dtype=torch.int16, device=dev) for _ in range(self.depth)]
+        self._keys_host = [torch.empty(self.cap, dtype=torch.int16).pin_memory() for _ in range(self.depth)]
+        self._off_host = [torch.empty(n_off, dtype=torch.int64).pin_memory() for _ in range(self.depth)]
+        self._done = [None] * self.depth
+        self._copied = [0] * self.depth
+        self._guess = max(1, min(self.cap, int(initial_keys)))
+        self._pushed = self._popped = 0
+
+    def push(self, res):
+        import ctypes as C
+        import torch
+        from ._lib import check, lib
+        from .streams import current_stream_ptr
+        if self._pushed - self._popped >= self.depth:
+            raise RuntimeError("every host slot holds an unread step: pop() first")
+        b = self._pushed % self.depth
+        self._pushed += 1
+        fs, ds, dm = self.params
+        n_dev = res.seg_offsets[-1:]                       # the step's event count, on the device
+        check(lib.dvs_keys_from_events_devn(C.c_void_p(res.events_raw.data_ptr()), C.c_void_p(n_dev.data_ptr()), self.cap,
+                                            int(self.dvs.cfg.uncoded), fs, ds, dm, C.c_void_p(self._keys_dev[b].data_ptr()),
+                                            current_stream_ptr()))
+        self._off_host[b].copy_(res.seg_offsets, non_blocking=True)
+        m = self._copied[b] = min(self.cap, self._guess)
+        self._keys_host[b][:m].copy_(self._keys_dev[b][:m], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._done[b] = ev
+
+    def pop(self):
+        """(offsets int64 [S * n_slots * 2 + 1], keys int16 [n]) of the oldest pushed step."""
+        if self._popped >= self._pushed:
+            raise RuntimeError("nothing pushed")
+        b = self._popped % self.depth
+        self._popped += 1
+        self._done[b].synchronize()
+        off = self._off_host[b].numpy()
+        n = int(off[-1])
+        if n > self.cap:
+            raise OverflowError("event buffer too small: call grow_events(capacity)")
+        if n > self._copied[b]:   # more than the sized copy brought over: fetch the rest now (and size the next ones up)
+            self._keys_host[b][self._copied[b]:n].copy_(self._keys_dev[b][self._copied[b]:n])
+        self._guess = max(self._guess, min(self.cap, 2 * n))
+        return off, self._keys_host[b].numpy()[:n]
