@@ -454,6 +454,49 @@ def test_random_configurations_against_the_oracle():
     assert undefined <= 12, "too many draws landed in the reference's undefined region: %d" % undefined
 
 
+def test_random_configurations_with_byte_state_and_padded_rows_against_the_oracle():
+    """A second seeded sweep over the layouts added at the end of round 2: one-byte state planes wherever they are
+    exact, row widths that are not a multiple of 8 pixels (padded planes with 2x2 / 4x4 inhibition, tile-aligned linear
+    kernels without), uint8 frames -- whatever the dispatch picks must reproduce the oracle bit for bit."""
+    rng = np.random.default_rng(2027)
+    undefined = 0
+    for trial in range(40):
+        W = int(rng.choice([12, 20, 36, 44, 64, 100, 128, 346, 348, 520]))
+        H = int(rng.choice([4, 8, 12, 16, 28]))
+        S = int(rng.choice([1, 2, 3, 4]))
+        out = str(rng.choice(["RATE", "RATE", "TIME", "TIME_BIN", "TIME_BIN_THR"]))
+        inh = int(rng.choice([0, 2, 2, 4])) if W % 4 == 0 else int(rng.choice([0, 2, 2]))
+        adaptive = bool(rng.integers(0, 2)) and out in ("RATE", "TIME", "TIME_BIN_THR")
+        uncoded = bool(rng.integers(0, 5) == 0)
+        byte_ok = not (adaptive and uncoded)
+        kw = dict(output_type=out, inh=inh, adaptive=adaptive, hw=float(rng.choice([1.0, 1.0, 0.99, 0.25])),
+                  polarity=int(rng.choice([0, 1, 2, 2, 3])), uncoded=uncoded,
+                  frame_dtype=str(rng.choice(["int16", "int16", "uint8"])), threshold=int(rng.choice([2, 5, 12, 40])),
+                  max_time_ms=int(rng.choice([2, 4, 8, 12])), source=str(rng.choice(["random", "bar", "narrow", "wide"])),
+                  seed=int(rng.integers(0, 1000)), split_lists=bool(rng.integers(0, 2)),
+                  force_generic=int(rng.choice([0, 0, 0, 1])), frames=3, debug=False,
+                  state_dtype="uint8" if (byte_ok and rng.integers(0, 4) != 0) else "int16")
+        if adaptive:
+            kw["thr0"] = int(rng.choice([0, 6, 12, 200]))
+        if kw["source"] == "wide" and kw["frame_dtype"] == "uint8":
+            kw["source"] = "random"   # (frames outside [0, 255] only exist as int16)
+        if kw["uncoded"] and kw["polarity"] == 3:
+            kw["polarity"] = 2
+        if out in ("TIME_BIN", "TIME_BIN_THR"):
+            kw["num_bins"] = 8 if out == "TIME_BIN" else 6
+            kw["max_time_ms"] = 8
+        elif out == "TIME":
+            kw["num_bins"] = kw["max_time_ms"]
+        try:
+            _run_case(S, H, W, **kw)
+        except IndexError:
+            undefined += 1
+            continue
+        except AssertionError:
+            raise AssertionError("trial %d failed: S=%d H=%d W=%d %r" % (trial, S, H, W, kw))
+    assert undefined <= 16, "too many draws landed in the reference's undefined region: %d" % undefined
+
+
 @pytest.mark.parametrize("state_dtype", ["int16", "uint8"])
 def test_inhibition_on_rows_that_are_not_a_multiple_of_eight_pixels_takes_the_fast_kernels(state_dtype):
     """DAVIS346-shaped streams (346 x 260) with 2x2 / 4x4 inhibition: the planes are kept with rows padded to a multiple
